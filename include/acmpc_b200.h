@@ -1,0 +1,139 @@
+/*
+ * acmpc_b200.h -- C ABI of the B200-native MPC step (drop-in boundary).
+ *
+ * The reference (Adelaide-Autonomous-Racing-Kit/ac-mpc) is pure Python and has no FFI layer;
+ * the boundary a maintainer would bind is the object API of `acmpc.control`:
+ *
+ *   acmpc_create            <-> build_mpc / SpatialMPC.__init__      controller.py:19-29, spatial_mpc.py:21-58
+ *   acmpc_solve_batch_*     <-> SpatialMPC.get_control               spatial_mpc.py:170-217
+ *                               (construct_waypoints :125-154, compute_speed_profile :89-123,
+ *                                SpatialBicycleModel.t2s/linearise/s2t dynamics.py:23-103,
+ *                                ControlSolver.solve solvers/control.py:15-106,
+ *                                SpeedProfileSolver.solve solvers/speed_profile.py:15-86,131-150,
+ *                                and the `osqp` solve those two call)
+ *   acmpc_outputs fields    <-> the attributes get_control mutates    spatial_mpc.py:193-212
+ *   acmpc_destroy           <-> object lifetime
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  All floating point is IEEE binary64.
+ * Per-instance solver failure is reported in `status[]`, never through the return code; the return
+ * code is non-zero only for API misuse or CUDA errors (see acmpc_last_error).
+ */
+#ifndef ACMPC_B200_H
+#define ACMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACMPC_ABI_VERSION 1
+
+/* OSQP status codes written to status[] / status_speed[] ("solved" == 1, spatial_mpc.py:115,193) */
+#define ACMPC_SOLVED 1
+#define ACMPC_SOLVED_INACCURATE 2
+#define ACMPC_PRIMAL_INFEASIBLE_INACCURATE 3
+#define ACMPC_DUAL_INFEASIBLE_INACCURATE 4
+#define ACMPC_MAX_ITER_REACHED (-2)
+#define ACMPC_PRIMAL_INFEASIBLE (-3)
+#define ACMPC_DUAL_INFEASIBLE (-4)
+#define ACMPC_NON_CVX (-7)
+#define ACMPC_UNSOLVED (-10)
+
+/* return codes */
+#define ACMPC_OK 0
+#define ACMPC_ERR_INVALID 1     /* bad argument / unsupported horizon */
+#define ACMPC_ERR_CUDA 2        /* CUDA runtime error, text in acmpc_last_error */
+#define ACMPC_ERR_NO_DEVICE 3   /* no sm_100 device: there is NO CPU fallback */
+
+#define ACMPC_MIN_HORIZON 4
+#define ACMPC_MAX_HORIZON 128
+
+typedef struct acmpc_config {
+    int32_t horizon;            /* H = config["horizon"]; n = H-1 stages          spatial_mpc.py:27 */
+    int32_t max_iter;           /* MAX_SOLVER_ITERATIONS = 4000                   spatial_mpc.py:17 */
+    /* config["speed_profile_constraints"]                                        spatial_mpc.py:36 */
+    double v_min, v_max, a_min, a_max, ay_max, ki_min, end_velocity;
+    int32_t has_end_velocity;   /* 0 <=> end_velocity: null                       speed_profile.py:42 */
+    int32_t reserved0;
+    double step_cost[3];        /* Q  = diag(step_cost)   e_y, e_psi, t           solvers/control.py:126 */
+    double r_term[2];           /* R  = diag(r_term)      v, kappa_cmd            solvers/control.py:127 */
+    double final_cost[3];       /* QN = diag(final_cost)                          solvers/control.py:128 */
+    /* vehicle_data.vehicle_data.wheelbase / .width, max_steering_angle()         dynamics.py:11-13 */
+    double wheelbase, width, delta_max;
+    /* build-time velocity limits that become the input bounds min_u/max_u        controller.py:20-24 */
+    double input_v_min, input_v_max;
+    /* OSQP settings; the reference leaves all of them at the library defaults */
+    double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
+    int32_t scaling;               /* Ruiz passes, 10 */
+    int32_t check_termination;     /* 25 */
+    int32_t adaptive_rho;          /* 1 */
+    int32_t adaptive_rho_interval; /* fixed iteration interval, default 50 */
+} acmpc_config;
+
+/* Result arrays, one slice per instance.  Any pointer may be NULL (field not written).
+ * n = H-1.  For the *_device entry point these are device pointers, for *_host host pointers. */
+typedef struct acmpc_outputs {
+    double *controls;       /* [B,2,n] row 0 = v_k, row 1 = delta_k = atan(kappa_cmd_k * L)   projected_control */
+    double *prediction;     /* [B,n,2] (X_k, Y_k) world-frame rollout (s2t)                  current_prediction */
+    double *cum_time;       /* [B,n]   t_k                                                    cum_time */
+    double *states;         /* [B,H,3] spatial states x_0..x_{H-1} = dec.x[:3H] */
+    double *v_ref;          /* [B,n]   speed profile (zeros if the speed QP was not "solved") */
+    double *cost;           /* [B]     OSQP info.obj_val of the control QP = 1/2 x'Px + q'x */
+    double *pri_res;        /* [B]     control QP primal residual (unscaled, inf-norm) */
+    double *dua_res;        /* [B]     control QP dual residual */
+    int32_t *status;        /* [B]     control QP status */
+    int32_t *status_speed;  /* [B]     speed-profile QP status */
+    int32_t *iters;         /* [B,2]   ADMM iterations: speed QP, control QP */
+    int32_t *rho_updates;   /* [B,2]   refactorisations caused by adaptive rho */
+} acmpc_outputs;
+
+typedef struct acmpc_handle acmpc_handle;
+
+int32_t acmpc_abi_version(void);
+
+/* Fill *cfg with the OSQP defaults, the Monza racing block (configs/monza.yaml:67-81) and the
+ * documented synthetic vehicle constants (wheelbase 2.65 m, width 1.99 m, delta_max 0.30 rad). */
+void acmpc_default_config(acmpc_config *cfg);
+
+/* Create a solver bound to CUDA device `device`.  Fails with ACMPC_ERR_NO_DEVICE when no CUDA
+ * device is present: the product has no CPU path. */
+int32_t acmpc_create(const acmpc_config *cfg, int32_t device, acmpc_handle **out);
+int32_t acmpc_destroy(acmpc_handle *h);
+const char *acmpc_last_error(const acmpc_handle *h);
+
+/* bytes of one instance's packed warm-start record (scaled x,z,y + rho of both QPs) */
+int64_t acmpc_warm_stride(const acmpc_handle *h);
+
+/* One MPC step for B independent instances, everything resident on the device.
+ *   d_paths   [B,H,3] rows (x, y, width) in the ego frame (x right, y forward)   get_control arg 1
+ *   d_offsets [B] lateral offset (get_control arg 3) or NULL (= 0.0)
+ *   d_vmax    [B] live speed_profile_constraints["v_max"] (controller.py:241-243) or NULL (= cfg.v_max)
+ *   is_localised: get_control arg 2
+ *   d_warm    NULL = cold start (x=z=y=0, rho=cfg.rho) ; else [B, acmpc_warm_stride] bytes, read
+ *             when warm_valid != 0 and always rewritten (the reference's persistent OSQP objects)
+ *   stream    cudaStream_t (NULL = default stream).  Asynchronous: no host sync inside. */
+int32_t acmpc_solve_batch_device(acmpc_handle *h, int32_t B, const double *d_paths,
+                                 const double *d_offsets, const double *d_vmax,
+                                 int32_t is_localised, void *d_warm, int32_t warm_valid,
+                                 const acmpc_outputs *d_out, void *stream);
+
+/* Same with HOST buffers: copies inputs to the device, runs the kernel, copies every non-NULL
+ * output back and synchronises.  (Warm-start records stay on the device inside the handle when
+ * keep_warm != 0: this is the B=1 path the drop-in SpatialMPC.get_control uses.) */
+int32_t acmpc_solve_batch_host(acmpc_handle *h, int32_t B, const double *paths,
+                               const double *offsets, const double *vmax, int32_t is_localised,
+                               int32_t keep_warm, const acmpc_outputs *out);
+
+/* Counters of the last launch: kernel launches issued and dynamic shared memory per CTA. */
+int32_t acmpc_last_launch_info(const acmpc_handle *h, int32_t *n_launches, int32_t *smem_bytes,
+                               int32_t *threads_per_cta, int32_t *instances_per_cta);
+
+/* FP64 FMA micro-benchmark (dependent-chain-free DFMA loop on every SM): the roofline
+ * denominator for this path, MEASURED_PEAKS.json has no FP64 figure.  Returns TFLOP/s. */
+int32_t acmpc_fp64_peak_tflops(int32_t device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACMPC_B200_H */

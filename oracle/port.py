@@ -1,0 +1,325 @@
+"""ctypes bindings of the CPU oracle (oracle/_build/liboracle.so).
+
+TEST INFRASTRUCTURE, NOT PRODUCT CODE: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.  PARITY UNPINNED (see osqp_port.h).
+
+Two layers are exposed:
+  * `PortOSQP`   -- the OSQP restatement for a general sparse QP (osqp_port.c); the shim package
+                    oracle/shim/osqp wraps it in the `osqp.OSQP` object API the reference calls
+                    (/root/reference/src/acmpc/control/solvers/control.py:88-106).
+  * `PortMPC`    -- one SpatialMPC.get_control (acmpc_port.c), single instance (optionally warm)
+                    or a multi-threaded cold-start batch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+STATUS_STRINGS = {
+    1: "solved",
+    2: "solved inaccurate",
+    3: "primal infeasible inaccurate",
+    4: "dual infeasible inaccurate",
+    -2: "maximum iterations reached",
+    -3: "primal infeasible",
+    -4: "dual infeasible",
+    -7: "problem non convex",
+    -10: "unsolved",
+}
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc only) and return the .so path."""
+    srcs = [os.path.join(_HERE, f) for f in ("osqp_port.c", "acmpc_port.c", "osqp_port.h")]
+    srcs.append(os.path.join(_HERE, "..", "include", "acmpc_b200.h"))
+    stale = force or not os.path.exists(_LIB_PATH)
+    if not stale:
+        t = os.path.getmtime(_LIB_PATH)
+        stale = any(os.path.exists(s) and os.path.getmtime(s) > t for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+class Settings(C.Structure):
+    _fields_ = [
+        ("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
+        ("eps_abs", C.c_double), ("eps_rel", C.c_double),
+        ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
+        ("adaptive_rho_tolerance", C.c_double),
+        ("scaling", C.c_int), ("max_iter", C.c_int), ("check_termination", C.c_int),
+        ("adaptive_rho", C.c_int), ("adaptive_rho_interval", C.c_int),
+        ("warm_start", C.c_int), ("scaled_termination", C.c_int),
+    ]
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("status", C.c_int), ("iter", C.c_int), ("rho_updates", C.c_int),
+        ("obj_val", C.c_double), ("pri_res", C.c_double), ("dua_res", C.c_double),
+        ("rho_estimate", C.c_double),
+    ]
+
+
+class Config(C.Structure):
+    """Mirror of `acmpc_config` (include/acmpc_b200.h)."""
+
+    _fields_ = [
+        ("horizon", C.c_int32), ("max_iter", C.c_int32),
+        ("v_min", C.c_double), ("v_max", C.c_double), ("a_min", C.c_double), ("a_max", C.c_double),
+        ("ay_max", C.c_double), ("ki_min", C.c_double), ("end_velocity", C.c_double),
+        ("has_end_velocity", C.c_int32), ("reserved0", C.c_int32),
+        ("step_cost", C.c_double * 3), ("r_term", C.c_double * 2), ("final_cost", C.c_double * 3),
+        ("wheelbase", C.c_double), ("width", C.c_double), ("delta_max", C.c_double),
+        ("input_v_min", C.c_double), ("input_v_max", C.c_double),
+        ("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
+        ("eps_abs", C.c_double), ("eps_rel", C.c_double),
+        ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
+        ("adaptive_rho_tolerance", C.c_double),
+        ("scaling", C.c_int32), ("check_termination", C.c_int32),
+        ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32),
+    ]
+
+
+class Outputs(C.Structure):
+    """Mirror of `acmpc_outputs`."""
+
+    _fields_ = [
+        ("controls", C.c_void_p), ("prediction", C.c_void_p), ("cum_time", C.c_void_p),
+        ("states", C.c_void_p), ("v_ref", C.c_void_p), ("cost", C.c_void_p),
+        ("pri_res", C.c_void_p), ("dua_res", C.c_void_p), ("status", C.c_void_p),
+        ("status_speed", C.c_void_p), ("iters", C.c_void_p), ("rho_updates", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int)
+        L.opq_default_settings.argtypes = [C.POINTER(Settings)]
+        L.opq_setup.restype = C.c_void_p
+        L.opq_setup.argtypes = [C.c_int, C.c_int, ip, ip, dp, dp, ip, ip, dp, dp, dp, C.POINTER(Settings)]
+        L.opq_free.argtypes = [C.c_void_p]
+        L.opq_update.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        L.opq_update.restype = C.c_int
+        L.opq_cold_start.argtypes = [C.c_void_p]
+        L.opq_warm_start.argtypes = [C.c_void_p, dp, dp]
+        L.opq_solve.argtypes = [C.c_void_p, dp, dp, C.POINTER(Info)]
+        L.opq_solve.restype = C.c_int
+        L.opq_get_vec.restype = dp
+        L.opq_get_vec.argtypes = [C.c_void_p, C.c_char_p, ip]
+        L.opq_get_scalar.restype = C.c_double
+        L.opq_get_scalar.argtypes = [C.c_void_p, C.c_char_p]
+        L.acmpc_port_create.restype = C.c_void_p
+        L.acmpc_port_create.argtypes = [C.POINTER(Config)]
+        L.acmpc_port_destroy.argtypes = [C.c_void_p]
+        L.acmpc_port_step.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(Outputs)]
+        L.acmpc_port_step.restype = C.c_int
+        L.acmpc_port_solve_batch.argtypes = [C.POINTER(Config), C.c_int, dp, dp, dp, C.c_int, C.c_int, C.POINTER(Outputs)]
+        L.acmpc_port_solve_batch.restype = C.c_int
+        L.acmpc_port_default_config.argtypes = [C.POINTER(Config)]
+        L.acmpc_port_waypoints.restype = dp
+        L.acmpc_port_waypoints.argtypes = [C.c_void_p]
+        L.acmpc_port_get_qp.argtypes = [C.c_void_p, C.c_int, ip, ip, C.POINTER(ip), C.POINTER(ip),
+                                        C.POINTER(dp), C.POINTER(dp), C.POINTER(dp), C.POINTER(dp), C.POINTER(dp)]
+        _lib = L
+    return _lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def default_settings(**kw) -> Settings:
+    s = Settings()
+    lib().opq_default_settings(C.byref(s))
+    for k, v in kw.items():
+        if not hasattr(s, k):
+            raise TypeError(f"unknown OSQP setting {k!r}")
+        setattr(s, k, v)
+    return s
+
+
+class PortOSQP:
+    """General sparse QP through the C restatement.  P: any scipy sparse (upper triangle is used)."""
+
+    def __init__(self, P, q, A, l, u, **settings):
+        from scipy import sparse
+
+        L = lib()
+        P = sparse.triu(sparse.csc_matrix(P), format="csc")
+        A = sparse.csc_matrix(A)
+        P.sort_indices()
+        A.sort_indices()
+        self.n, self.m = A.shape[1], A.shape[0]
+        self._Pp = np.ascontiguousarray(P.indptr, dtype=np.intc)
+        self._Pi = np.ascontiguousarray(P.indices, dtype=np.intc)
+        self._Px = np.ascontiguousarray(P.data, dtype=np.float64)
+        self._Ap = np.ascontiguousarray(A.indptr, dtype=np.intc)
+        self._Ai = np.ascontiguousarray(A.indices, dtype=np.intc)
+        self._Ax = np.ascontiguousarray(A.data, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        l = np.ascontiguousarray(l, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        self.settings = default_settings(**settings)
+        self._w = L.opq_setup(self.n, self.m, _iptr(self._Pp), _iptr(self._Pi), _dptr(self._Px), _dptr(q),
+                              _iptr(self._Ap), _iptr(self._Ai), _dptr(self._Ax), _dptr(l), _dptr(u),
+                              C.byref(self.settings))
+        if not self._w:
+            raise ValueError("opq_setup failed (singular KKT?)")
+
+    def __del__(self):
+        if getattr(self, "_w", None):
+            lib().opq_free(self._w)
+            self._w = None
+
+    def update(self, q=None, l=None, u=None, Ax=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (q, l, u, Ax)]
+        if arrs[3] is not None and arrs[3].shape[0] != self._Ax.shape[0]:
+            raise ValueError("Ax has the wrong number of stored entries")
+        rc = lib().opq_update(self._w, *[_dptr(a) for a in arrs])
+        if rc != 0:
+            raise ValueError("lower bound must be lower than or equal to upper bound / refactor failed")
+
+    def cold_start(self):
+        lib().opq_cold_start(self._w)
+
+    def warm_start(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        lib().opq_warm_start(self._w, _dptr(x), _dptr(y))
+
+    def solve(self):
+        x = np.empty(self.n)
+        y = np.empty(self.m)
+        info = Info()
+        lib().opq_solve(self._w, _dptr(x), _dptr(y), C.byref(info))
+        return x, y, info
+
+    def vec(self, name: str) -> np.ndarray:
+        ln = C.c_int(0)
+        p = lib().opq_get_vec(self._w, name.encode(), C.byref(ln))
+        return np.ctypeslib.as_array(p, shape=(ln.value,)).copy()
+
+    def scalar(self, name: str) -> float:
+        return lib().opq_get_scalar(self._w, name.encode())
+
+
+def default_config(**kw) -> Config:
+    c = Config()
+    lib().acmpc_port_default_config(C.byref(c))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise TypeError(f"unknown config field {k!r}")
+        if k in ("step_cost", "r_term", "final_cost"):
+            arr = getattr(c, k)
+            for i, x in enumerate(v):
+                arr[i] = float(x)
+        else:
+            setattr(c, k, v)
+    return c
+
+
+OUTPUT_SPEC = {
+    # name: (per-instance shape as a function of (H, n), dtype)
+    "controls": (lambda H, n: (2, n), np.float64),
+    "prediction": (lambda H, n: (n, 2), np.float64),
+    "cum_time": (lambda H, n: (n,), np.float64),
+    "states": (lambda H, n: (H, 3), np.float64),
+    "v_ref": (lambda H, n: (n,), np.float64),
+    "cost": (lambda H, n: (), np.float64),
+    "pri_res": (lambda H, n: (), np.float64),
+    "dua_res": (lambda H, n: (), np.float64),
+    "status": (lambda H, n: (), np.int32),
+    "status_speed": (lambda H, n: (), np.int32),
+    "iters": (lambda H, n: (2,), np.int32),
+    "rho_updates": (lambda H, n: (2,), np.int32),
+}
+
+
+def alloc_outputs(B: int, H: int):
+    n = H - 1
+    arrs = {k: np.zeros((B,) + shp(H, n), dtype=dt) for k, (shp, dt) in OUTPUT_SPEC.items()}
+    o = Outputs()
+    for k, a in arrs.items():
+        setattr(o, k, a.ctypes.data)
+    return arrs, o
+
+
+class PortMPC:
+    """One stateful SpatialMPC restated in C (acmpc_port.c)."""
+
+    def __init__(self, cfg: Config):
+        self.cfg = cfg
+        self.H = cfg.horizon
+        self._p = lib().acmpc_port_create(C.byref(cfg))
+        if not self._p:
+            raise ValueError("acmpc_port_create failed")
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib().acmpc_port_destroy(self._p)
+            self._p = None
+
+    def step(self, path, offset=0.0, v_max=None, is_localised=False, warm=False):
+        path = np.ascontiguousarray(path, dtype=np.float64)
+        assert path.shape == (self.H, 3)
+        arrs, o = alloc_outputs(1, self.H)
+        lib().acmpc_port_step(self._p, _dptr(path), float(offset),
+                              float(self.cfg.v_max if v_max is None else v_max),
+                              int(bool(is_localised)), int(bool(warm)), C.byref(o))
+        return {k: v[0] for k, v in arrs.items()}
+
+    def waypoints(self) -> np.ndarray:
+        n = self.H - 1
+        p = lib().acmpc_port_waypoints(self._p)
+        return np.ctypeslib.as_array(p, shape=(7, n)).copy()
+
+    def qp(self, which: str):
+        """QP data of the last step: which in {"speed", "control"} -> dict(A (csc), Pdiag, q, l, u)."""
+        from scipy import sparse
+
+        n, m = C.c_int(), C.c_int()
+        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        Ap, Ai, Ax, Pd, q, l, u = ip(), ip(), dp(), dp(), dp(), dp(), dp()
+        lib().acmpc_port_get_qp(self._p, 0 if which == "speed" else 1, C.byref(n), C.byref(m),
+                                C.byref(Ap), C.byref(Ai), C.byref(Ax), C.byref(Pd), C.byref(q),
+                                C.byref(l), C.byref(u))
+        n, m = n.value, m.value
+        indptr = np.ctypeslib.as_array(Ap, shape=(n + 1,)).copy()
+        nnz = int(indptr[-1])
+        A = sparse.csc_matrix((np.ctypeslib.as_array(Ax, shape=(nnz,)).copy(),
+                               np.ctypeslib.as_array(Ai, shape=(nnz,)).copy(), indptr), shape=(m, n))
+        g = lambda p_, k: np.ctypeslib.as_array(p_, shape=(k,)).copy()
+        return dict(A=A, Pdiag=g(Pd, n), q=g(q, n), l=g(l, m), u=g(u, m))
+
+
+def solve_batch(cfg: Config, paths, offsets=None, vmax=None, is_localised=False, nthreads=1):
+    """Cold-start batch on `nthreads` host threads; returns dict of numpy arrays."""
+    paths = np.ascontiguousarray(paths, dtype=np.float64)
+    B, H, _ = paths.shape
+    assert H == cfg.horizon
+    offsets = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.float64)
+    vmax = None if vmax is None else np.ascontiguousarray(vmax, dtype=np.float64)
+    arrs, o = alloc_outputs(B, H)
+    rc = lib().acmpc_port_solve_batch(C.byref(cfg), B, _dptr(paths), _dptr(offsets), _dptr(vmax),
+                                      int(bool(is_localised)), int(nthreads), C.byref(o))
+    if rc != 0:
+        raise RuntimeError("acmpc_port_solve_batch failed")
+    return arrs
