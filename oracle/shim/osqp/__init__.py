@@ -36,6 +36,9 @@ class OSQP:
     def solve(self):
         x, y, info = self._solver.solve()
         status = _port.STATUS_STRINGS[info.status]
+        _RECORD.append(("solve", dict(x=x.copy(), n=self._solver.n, m=self._solver.m, status_val=info.status,
+                                      iter=info.iter, obj_val=info.obj_val, pri_res=info.pri_res,
+                                      dua_res=info.dua_res, rho_updates=info.rho_updates)))
         if info.status in (-3, 3, -4, 4, -7):
             x = np.full_like(x, np.nan)
             y = np.full_like(y, np.nan)
