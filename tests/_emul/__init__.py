@@ -1,0 +1,40 @@
+"""TEST-ONLY: ctypes loader of the one-lane CPU emulation of the kernel body (see emul.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle import port
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libacmpc_emul.so")
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(_HERE, "emul.cpp"), os.path.join(_ROOT, "ac_mpc_b200", "csrc", "mpc_body.cuh"),
+                os.path.join(_ROOT, "include", "acmpc_b200.h")]
+        if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+            subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", "-o", _SO, srcs[0]],
+                           check=True, capture_output=True)
+        _lib = C.CDLL(_SO)
+        dp = C.POINTER(C.c_double)
+        _lib.acmpc_emul_solve_batch.argtypes = [C.POINTER(port.Config), C.c_int, dp, dp, dp, C.c_int,
+                                                C.POINTER(port.Outputs)]
+    return _lib
+
+
+def solve_batch(cfg, paths, offsets=None, vmax=None, is_localised=False):
+    paths = np.ascontiguousarray(paths, dtype=np.float64)
+    B, H, _ = paths.shape
+    offsets = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.float64)
+    vmax = None if vmax is None else np.ascontiguousarray(vmax, dtype=np.float64)
+    arrs, o = port.alloc_outputs(B, H)
+    rc = lib().acmpc_emul_solve_batch(C.byref(cfg), B, port._dptr(paths), port._dptr(offsets), port._dptr(vmax),
+                                      int(bool(is_localised)), C.byref(o))
+    assert rc == 0
+    return arrs
