@@ -1,0 +1,156 @@
+"""ctypes binding of the C ABI in include/acmpc_b200.h (ac_mpc_b200/csrc/libacmpc_b200.so).
+
+The library is CUDA-only.  If it cannot be loaded, or no sm_100 device is present when a solver is
+created, this module raises: there is no CPU fallback anywhere in the package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libacmpc_b200.so")
+_SOURCES = [os.path.join(CSRC, "acmpc_b200.cu"), os.path.join(CSRC, "mpc_body.cuh"),
+            os.path.join(os.path.dirname(_HERE), "include", "acmpc_b200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# symbols declared in include/acmpc_b200.h
+EXPORTED = [
+    "acmpc_abi_version", "acmpc_default_config", "acmpc_create", "acmpc_destroy", "acmpc_last_error",
+    "acmpc_warm_stride", "acmpc_solve_batch_device", "acmpc_solve_batch_host", "acmpc_last_launch_info",
+    "acmpc_fp64_peak_tflops",
+]
+
+RC_NAMES = {0: "ACMPC_OK", 1: "ACMPC_ERR_INVALID", 2: "ACMPC_ERR_CUDA", 3: "ACMPC_ERR_NO_DEVICE"}
+STATUS_STRINGS = {
+    1: "solved", 2: "solved inaccurate", 3: "primal infeasible inaccurate", 4: "dual infeasible inaccurate",
+    -2: "maximum iterations reached", -3: "primal infeasible", -4: "dual infeasible",
+    -7: "problem non convex", -10: "unsolved",
+}
+
+
+class Config(C.Structure):
+    """`acmpc_config`."""
+
+    _fields_ = [
+        ("horizon", C.c_int32), ("max_iter", C.c_int32),
+        ("v_min", C.c_double), ("v_max", C.c_double), ("a_min", C.c_double), ("a_max", C.c_double),
+        ("ay_max", C.c_double), ("ki_min", C.c_double), ("end_velocity", C.c_double),
+        ("has_end_velocity", C.c_int32), ("reserved0", C.c_int32),
+        ("step_cost", C.c_double * 3), ("r_term", C.c_double * 2), ("final_cost", C.c_double * 3),
+        ("wheelbase", C.c_double), ("width", C.c_double), ("delta_max", C.c_double),
+        ("input_v_min", C.c_double), ("input_v_max", C.c_double),
+        ("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
+        ("eps_abs", C.c_double), ("eps_rel", C.c_double),
+        ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
+        ("adaptive_rho_tolerance", C.c_double),
+        ("scaling", C.c_int32), ("check_termination", C.c_int32),
+        ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32),
+    ]
+
+
+OUTPUT_FIELDS = ["controls", "prediction", "cum_time", "states", "v_ref", "cost", "pri_res", "dua_res",
+                 "status", "status_speed", "iters", "rho_updates", "waypoints"]
+
+
+class Outputs(C.Structure):
+    """`acmpc_outputs`."""
+
+    _fields_ = [(name, C.c_void_p) for name in OUTPUT_FIELDS]
+
+
+def output_spec(H: int):
+    """name -> (per-instance shape, numpy dtype string) in ABI order."""
+    n = H - 1
+    return {
+        "controls": ((2, n), "float64"), "prediction": ((n, 2), "float64"), "cum_time": ((n,), "float64"),
+        "states": ((H, 3), "float64"), "v_ref": ((n,), "float64"), "cost": ((), "float64"),
+        "pri_res": ((), "float64"), "dua_res": ((), "float64"), "status": ((), "int32"),
+        "status_speed": ((), "int32"), "iters": ((2,), "int32"), "rho_updates": ((2,), "int32"),
+        "waypoints": ((7, n), "float64"),
+    }
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a in-tree with nvcc (cross-compiles without a GPU)."""
+    stale = force or not os.path.exists(LIB_PATH)
+    if not stale:
+        t = os.path.getmtime(LIB_PATH)
+        stale = any(os.path.getmtime(s) > t for s in _SOURCES)
+    if stale:
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, _SOURCES[0]]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        if verbose:
+            print(r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise loudly if it is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"ac_mpc_b200: CUDA extension {LIB_PATH} is missing. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc); there is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    for name in EXPORTED:
+        if not hasattr(L, name):
+            raise RuntimeError(f"ac_mpc_b200: {LIB_PATH} does not export {name}")
+    dp, vp = C.POINTER(C.c_double), C.c_void_p
+    L.acmpc_abi_version.restype = C.c_int32
+    L.acmpc_default_config.argtypes = [C.POINTER(Config)]
+    L.acmpc_default_config.restype = None
+    L.acmpc_create.argtypes = [C.POINTER(Config), C.c_int32, C.POINTER(vp)]
+    L.acmpc_create.restype = C.c_int32
+    L.acmpc_destroy.argtypes = [vp]
+    L.acmpc_destroy.restype = C.c_int32
+    L.acmpc_last_error.argtypes = [vp]
+    L.acmpc_last_error.restype = C.c_char_p
+    L.acmpc_warm_stride.argtypes = [vp]
+    L.acmpc_warm_stride.restype = C.c_int64
+    L.acmpc_solve_batch_device.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, C.c_int32,
+                                           C.POINTER(Outputs), vp]
+    L.acmpc_solve_batch_device.restype = C.c_int32
+    L.acmpc_solve_batch_host.argtypes = [vp, C.c_int32, dp, dp, dp, C.c_int32, C.c_int32, C.POINTER(Outputs)]
+    L.acmpc_solve_batch_host.restype = C.c_int32
+    L.acmpc_last_launch_info.argtypes = [vp] + [C.POINTER(C.c_int32)] * 4
+    L.acmpc_last_launch_info.restype = C.c_int32
+    L.acmpc_fp64_peak_tflops.argtypes = [C.c_int32, dp]
+    L.acmpc_fp64_peak_tflops.restype = C.c_int32
+    _lib = L
+    return L
+
+
+def default_config(**overrides) -> Config:
+    cfg = Config()
+    load().acmpc_default_config(C.byref(cfg))
+    apply_overrides(cfg, overrides)
+    return cfg
+
+
+def apply_overrides(cfg: Config, overrides: dict) -> Config:
+    for k, v in overrides.items():
+        if not any(k == f[0] for f in Config._fields_):
+            raise TypeError(f"unknown acmpc_config field {k!r}")
+        if k in ("step_cost", "r_term", "final_cost"):
+            arr = getattr(cfg, k)
+            if len(v) != len(arr):
+                raise ValueError(f"{k} needs {len(arr)} entries")
+            for i, x in enumerate(v):
+                arr[i] = float(x)
+        else:
+            setattr(cfg, k, v)
+    return cfg

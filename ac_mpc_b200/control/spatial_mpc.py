@@ -1,0 +1,123 @@
+"""Drop-in mirror of the reference's `SpatialMPC` (/root/reference/src/acmpc/control/spatial_mpc.py:20-217)
+on top of the CUDA library.  Same constructor arguments, same `get_control` signature, and results
+delivered as the same mutated attributes the caller reads (controller.py:274-280):
+`projected_control (2,n)`, `current_prediction (n,2)`, `cum_time (n,)`, `times`, `accelerations`,
+`steer_rates`, `reference_path`, `speed_profile`, `infeasibility_counter`.
+
+`get_control` is the B = 1 case of `get_control_batch`; both run the fused sm_100a kernel.  There is
+no host-side solver: without a B200 the call raises.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, Optional
+
+import numpy as np
+
+from .. import _capi
+from ..solver import BatchedMPC, config_from_reference
+from .paths import ReferencePath
+
+try:  # the reference logs through loguru; fall back to logging if it is absent
+    from loguru import logger
+except Exception:  # pragma: no cover
+    import logging
+
+    logger = logging.getLogger("ac_mpc_b200")
+
+MAX_SOLVER_ITERATIONS_MAP = 40000
+MAX_SOLVER_ITERATIONS = 4000
+
+
+class SpatialMPC:
+    def __init__(self, config: Dict, model, device: int = 0, **osqp_overrides):
+        self.MPC_horizon = config["horizon"]
+        self.cum_time = np.zeros((1))
+        self.model = model
+        self.nx = 3
+        self.nu = 2
+        # live dict, mutated by the caller before every step (controller.py:241-243)
+        self.speed_profile_constraints = config["speed_profile_constraints"]
+        self.ay_max = self.speed_profile_constraints["ay_max"]
+        self.delta_max = model.delta_max
+        self.current_prediction = None
+        self.infeasibility_counter = 0
+        self.projected_control = np.zeros((self.nu, self.MPC_horizon))
+        self._config = copy.deepcopy(config)
+        self._config["max_iterations"] = MAX_SOLVER_ITERATIONS
+        self._device = device
+        self._osqp_overrides = dict(osqp_overrides)
+        self._solver: Optional[BatchedMPC] = None      # created lazily (fork safety, controller.py:293)
+        self._solver_key = None
+        self.last_info: Dict = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _batched(self) -> BatchedMPC:
+        """(Re)build the native handle when a constraint other than v_max was edited in place."""
+        spc = self.speed_profile_constraints
+        key = tuple((k, spc.get(k)) for k in ("v_min", "a_min", "a_max", "ay_max", "ki_min", "end_velocity"))
+        if self._solver is None or key != self._solver_key:
+            cfg_dict = dict(self._config)
+            cfg_dict["speed_profile_constraints"] = dict(spc)
+            cfg = config_from_reference(cfg_dict, self.model, **self._osqp_overrides)
+            # input bounds keep the model's build-time limits (dynamics.py:15-20)
+            cfg.input_v_min, cfg.input_v_max = float(self.model.min_velocity), float(self.model.max_velocity)
+            if self._solver is not None:
+                self._solver.close()
+            self._solver = BatchedMPC(cfg, self._device)
+            self._solver_key = key
+        return self._solver
+
+    def get_control_batch(self, reference_paths, offsets=None, v_max=None, is_localised: bool = False,
+                          fields=None, out=None) -> Dict[str, np.ndarray]:
+        """B independent MPC steps: reference_paths (B,H,3), offsets (B,), v_max (B,) -> dict of arrays
+        (fields of `acmpc_outputs`).  Cold start per instance.  `out`: optional preallocated (e.g. pinned)
+        host arrays from `BatchedMPC.alloc_host_outputs`."""
+        solver = self._batched()
+        paths = np.ascontiguousarray(reference_paths, dtype=np.float64)
+        B = paths.shape[0]
+        if v_max is None:
+            v_max = np.full(B, float(self.speed_profile_constraints["v_max"]))
+        return solver.solve_host(paths, offsets, v_max, is_localised, out=out, fields=fields)
+
+    def get_control(self, reference_path: np.ndarray, is_localised: bool = False, offset: float = 0.0):
+        """One MPC step; signature and side effects of spatial_mpc.py:170-217."""
+        path = np.ascontiguousarray(reference_path, dtype=np.float64)[None]
+        out = self.get_control_batch(path, np.array([float(offset)]), None, is_localised)
+        n = self.MPC_horizon - 1
+        status, status_speed = int(out["status"][0]), int(out["status_speed"][0])
+        self.last_info = dict(status=_capi.STATUS_STRINGS.get(status, str(status)),
+                              status_speed=_capi.STATUS_STRINGS.get(status_speed, str(status_speed)),
+                              iters=out["iters"][0].tolist(), rho_updates=out["rho_updates"][0].tolist(),
+                              cost=float(out["cost"][0]), pri_res=float(out["pri_res"][0]),
+                              dua_res=float(out["dua_res"][0]))
+        waypoints = ReferencePath(n, out["waypoints"][0].copy())
+        if status_speed == 1:
+            self.speed_profile = waypoints.velocities.copy()
+        else:
+            failed = np.hstack([waypoints.xs, waypoints.ys])
+            logger.warning("Infeasible problem! reference path:\n" + f"{failed}")
+        if status == 1:
+            self.projected_control = out["controls"][0].copy()
+            x = out["states"][0][:n]
+            self.current_prediction = out["prediction"][0].copy()
+            self.reference_path = waypoints
+            self.cum_time = x[:, 2].copy()
+            self.times = np.diff(x[:, 2])
+            self.accelerations = np.diff(x[:, 0]) / self.times      # sic: e_y column, spatial_mpc.py:210
+            self.steer_rates = np.diff(x[:, 1]) / self.times
+            self.infeasibility_counter = 0
+        else:
+            logger.warning(f"Infeasible problem! Failed {self.infeasibility_counter} time(s).")
+            self.infeasibility_counter += 1
+
+    # -- entry points of the whole-track profile: not built yet -----
+    def compute_map_speed_profile(self, reference_path, ay_max: float, a_min: float):
+        raise NotImplementedError(
+            "whole-track speed profile (spatial_mpc.py:60-87) is a 'next' row of the scope table; "
+            "it is not implemented on the GPU yet and there is deliberately no CPU fallback")
+
+    def compute_speed_profile(self, reference_path, is_localised: bool = False, end_vel=None):
+        raise NotImplementedError(
+            "stand-alone compute_speed_profile is fused into get_control on the GPU path "
+            "(speed profile = `v_ref` / `waypoints[6]` of the outputs)")

@@ -1,0 +1,414 @@
+// acmpc_b200.cu -- sm_100a kernel + C ABI (include/acmpc_b200.h) of the batched MPC step.
+//
+// One warp (one CTA of 32 threads) owns one problem instance; its (H,3) reference-path slice is
+// staged into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier), everything else
+// (waypoints, both QPs, ADMM iterates, factorisations) stays in that CTA's shared memory until the
+// results are written back.  The per-instance algorithm is in mpc_body.cuh.
+//
+// There is NO CPU path in this library: acmpc_create fails with ACMPC_ERR_NO_DEVICE without a GPU.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "mpc_body.cuh"
+
+namespace {
+
+struct KernelParams {
+    acmpc_config cfg;
+    const double* paths;
+    const double* offsets;
+    const double* vmax;
+    acmpc_outputs out;
+    int32_t B;
+    int32_t is_localised;
+    int32_t use_tma;
+    int32_t qp_doubles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Stage `bytes` (multiple of 16, both ends 16-byte aligned) global -> shared through the TMA engine.
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* mbar, int lane)
+{
+    const uint32_t bar = smem_u32(mbar);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(dst)),
+            "l"(src), "r"(bytes), "r"(bar)
+            : "memory");
+    }
+    __syncwarp();
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(32) acmpc_step_kernel(const __grid_constant__ KernelParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int H = p.cfg.horizon, n = H - 1;
+    acmpc::Ctx c;
+    c.S = reinterpret_cast<double*>(smem_raw);
+    c.H = H, c.n = n, c.Hs = H, c.lane = lane, c.cfg = &p.cfg;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(c.S + p.qp_doubles);
+    // the raw path slice lands at the start of the QP region: it is dead before the QP data is built
+    double* raw = c.f(acmpc::F_PATH_END);
+    const double* src = p.paths + (size_t)b * 3 * H;
+    if (p.use_tma) {
+        tma_load_1d(raw, src, (uint32_t)(3 * H * sizeof(double)), mbar, lane);
+    } else {
+        for (int i = lane; i < 3 * H; i += 32) raw[i] = src[i];
+        __syncwarp();
+    }
+    acmpc::InstanceOut o;
+    const acmpc_outputs& g = p.out;
+    o.controls = g.controls ? g.controls + (size_t)b * 2 * n : nullptr;
+    o.prediction = g.prediction ? g.prediction + (size_t)b * 2 * n : nullptr;
+    o.cum_time = g.cum_time ? g.cum_time + (size_t)b * n : nullptr;
+    o.states = g.states ? g.states + (size_t)b * 3 * H : nullptr;
+    o.v_ref = g.v_ref ? g.v_ref + (size_t)b * n : nullptr;
+    o.cost = g.cost ? g.cost + b : nullptr;
+    o.pri_res = g.pri_res ? g.pri_res + b : nullptr;
+    o.dua_res = g.dua_res ? g.dua_res + b : nullptr;
+    o.status = g.status ? g.status + b : nullptr;
+    o.status_speed = g.status_speed ? g.status_speed + b : nullptr;
+    o.iters = g.iters ? g.iters + (size_t)b * 2 : nullptr;
+    o.rho_updates = g.rho_updates ? g.rho_updates + (size_t)b * 2 : nullptr;
+    o.waypoints = g.waypoints ? g.waypoints + (size_t)b * 7 * n : nullptr;
+    const double offset = p.offsets ? p.offsets[b] : 0.0;
+    const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
+    acmpc::solve_instance(c, raw, offset, vmax, p.is_localised, o);
+}
+
+// FP64 FMA throughput probe: 8 independent chains per thread, no memory traffic.
+__global__ void fp64_peak_kernel(double* sink, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c), a1 = fma(a1, m, c), a2 = fma(a2, m, c), a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c), a5 = fma(a5, m, c), a6 = fma(a6, m, c), a7 = fma(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace
+
+struct acmpc_handle {
+    acmpc_config cfg;
+    int device;
+    int sm_count;
+    std::string err;
+    cudaStream_t stream;     // owned, used by the host entry point
+    // device arena for the host entry point
+    void* d_arena;
+    size_t arena_bytes;
+    int last_launches, last_smem, last_threads, last_ipc;
+};
+
+namespace {
+
+bool fail(acmpc_handle* h, cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return false;
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    if (h) h->err = buf;
+    return true;
+}
+
+bool valid_config(const acmpc_config* c, std::string* why)
+{
+    if (c->horizon < ACMPC_MIN_HORIZON || c->horizon > ACMPC_MAX_HORIZON) {
+        *why = "horizon out of range";
+        return false;
+    }
+    if (c->max_iter < 1 || c->scaling < 0 || c->check_termination < 0) {
+        *why = "bad iteration settings";
+        return false;
+    }
+    if (!(c->rho > 0) || !(c->sigma > 0) || !(c->alpha > 0 && c->alpha < 2)) {
+        *why = "bad rho/sigma/alpha";
+        return false;
+    }
+    if (!(c->wheelbase > 0) || !(c->width >= 0)) {
+        *why = "bad vehicle constants";
+        return false;
+    }
+    return true;
+}
+
+size_t smem_bytes_for(int H) { return sizeof(double) * (size_t)acmpc::kFieldsPerStage * H + 16; }
+
+int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offsets, const double* d_vmax,
+           int is_localised, const acmpc_outputs* d_out, cudaStream_t stream)
+{
+    KernelParams p;
+    memset(&p, 0, sizeof(p));
+    p.cfg = h->cfg;
+    p.paths = d_paths, p.offsets = d_offsets, p.vmax = d_vmax;
+    p.out = *d_out;
+    p.B = B, p.is_localised = is_localised ? 1 : 0;
+    const int H = h->cfg.horizon;
+    p.qp_doubles = acmpc::kFieldsPerStage * H;
+    // TMA bulk copies need 16-byte aligned ends and a size that is a multiple of 16
+    p.use_tma = ((3 * H * sizeof(double)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_paths) & 15) == 0);
+    const size_t smem = smem_bytes_for(H);
+    acmpc_step_kernel<<<B, 32, smem, stream>>>(p);
+    h->last_launches = 1, h->last_smem = (int)smem, h->last_threads = 32, h->last_ipc = 1;
+    if (fail(h, cudaGetLastError(), "kernel launch")) return ACMPC_ERR_CUDA;
+    return ACMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t acmpc_abi_version(void) { return ACMPC_ABI_VERSION; }
+
+void acmpc_default_config(acmpc_config* c)
+{
+    memset(c, 0, sizeof(*c));
+    c->horizon = 50, c->max_iter = 4000;
+    c->v_min = 8.0, c->v_max = 84.0, c->a_min = -1.3, c->a_max = 1.0;
+    c->ay_max = 5.5, c->ki_min = 0.005, c->end_velocity = 14.0, c->has_end_velocity = 1;
+    c->step_cost[0] = 4e-3, c->step_cost[1] = 5e-2, c->step_cost[2] = 0.0;
+    c->r_term[0] = 1e-2, c->r_term[1] = 10.0;
+    c->final_cost[0] = 1.0, c->final_cost[1] = 0.0, c->final_cost[2] = 0.1;
+    c->wheelbase = 2.65, c->width = 1.99, c->delta_max = 0.30;
+    c->input_v_min = 8.0, c->input_v_max = 84.0;
+    c->rho = 0.1, c->sigma = 1e-6, c->alpha = 1.6;
+    c->eps_abs = 1e-3, c->eps_rel = 1e-3, c->eps_prim_inf = 1e-4, c->eps_dual_inf = 1e-4;
+    c->adaptive_rho_tolerance = 5.0;
+    c->scaling = 10, c->check_termination = 25, c->adaptive_rho = 1, c->adaptive_rho_interval = 50;
+}
+
+int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out)
+{
+    if (!cfg || !out) return ACMPC_ERR_INVALID;
+    *out = nullptr;
+    std::string why;
+    if (!valid_config(cfg, &why)) return ACMPC_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return ACMPC_ERR_NO_DEVICE;
+    }
+    acmpc_handle* h = new (std::nothrow) acmpc_handle();
+    if (!h) return ACMPC_ERR_INVALID;
+    h->cfg = *cfg;
+    h->device = device;
+    h->d_arena = nullptr, h->arena_bytes = 0;
+    h->last_launches = h->last_smem = h->last_threads = h->last_ipc = 0;
+    cudaDeviceProp prop;
+    if (fail(h, cudaSetDevice(device), "cudaSetDevice") ||
+        fail(h, cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) {
+        delete h;
+        return ACMPC_ERR_CUDA;
+    }
+    if (prop.major != 10) {   // the fatbin only holds sm_100a code
+        delete h;
+        return ACMPC_ERR_NO_DEVICE;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    const size_t smem = smem_bytes_for(cfg->horizon);
+    if (smem > (size_t)prop.sharedMemPerBlockOptin ||
+        fail(h, cudaFuncSetAttribute(acmpc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+             "cudaFuncSetAttribute") ||
+        fail(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        delete h;
+        return ACMPC_ERR_CUDA;
+    }
+    *out = h;
+    return ACMPC_OK;
+}
+
+int32_t acmpc_destroy(acmpc_handle* h)
+{
+    if (!h) return ACMPC_OK;
+    cudaSetDevice(h->device);
+    if (h->d_arena) cudaFree(h->d_arena);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return ACMPC_OK;
+}
+
+const char* acmpc_last_error(const acmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int64_t acmpc_warm_stride(const acmpc_handle* h)
+{
+    (void)h;
+    return 0;   // warm-start records are not implemented in this ABI revision
+}
+
+int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_paths, const double* d_offsets,
+                                 const double* d_vmax, int32_t is_localised, void* d_warm, int32_t warm_valid,
+                                 const acmpc_outputs* d_out, void* stream)
+{
+    if (!h) return ACMPC_ERR_INVALID;
+    if (B < 0 || !d_out || (B > 0 && !d_paths)) {
+        h->err = "bad arguments";
+        return ACMPC_ERR_INVALID;
+    }
+    if (d_warm || warm_valid) {
+        h->err = "warm start is not implemented in this ABI revision";
+        return ACMPC_ERR_INVALID;
+    }
+    if (B == 0) return ACMPC_OK;
+    if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    return launch(h, B, d_paths, d_offsets, d_vmax, is_localised, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, const double* offsets,
+                               const double* vmax, int32_t is_localised, int32_t keep_warm,
+                               const acmpc_outputs* out)
+{
+    if (!h) return ACMPC_ERR_INVALID;
+    if (B < 0 || !out || (B > 0 && !paths)) {
+        h->err = "bad arguments";
+        return ACMPC_ERR_INVALID;
+    }
+    if (keep_warm) {
+        h->err = "warm start is not implemented in this ABI revision";
+        return ACMPC_ERR_INVALID;
+    }
+    if (B == 0) return ACMPC_OK;
+    if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    const int H = h->cfg.horizon, n = H - 1;
+    const size_t nb = (size_t)B;
+    // arena layout (all 16-byte aligned): inputs then one slab per output field
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align(off + bytes); return o; };
+    const size_t o_paths = take(nb * 3 * H * 8), o_off = take(nb * 8), o_vmax = take(nb * 8);
+    const size_t o_ctrl = take(nb * 2 * n * 8), o_pred = take(nb * 2 * n * 8), o_ct = take(nb * n * 8);
+    const size_t o_st = take(nb * 3 * H * 8), o_vr = take(nb * n * 8), o_cost = take(nb * 8);
+    const size_t o_pr = take(nb * 8), o_dr = take(nb * 8), o_stat = take(nb * 4), o_ss = take(nb * 4);
+    const size_t o_it = take(nb * 8), o_ru = take(nb * 8), o_wp = take(nb * 7 * n * 8);
+    if (off > h->arena_bytes) {
+        if (h->d_arena) cudaFree(h->d_arena);
+        h->d_arena = nullptr, h->arena_bytes = 0;
+        if (fail(h, cudaMalloc(&h->d_arena, off), "cudaMalloc(arena)")) return ACMPC_ERR_CUDA;
+        h->arena_bytes = off;
+    }
+    char* base = static_cast<char*>(h->d_arena);
+    cudaStream_t s = h->stream;
+    if (fail(h, cudaMemcpyAsync(base + o_paths, paths, nb * 3 * H * 8, cudaMemcpyHostToDevice, s), "H2D paths"))
+        return ACMPC_ERR_CUDA;
+    if (offsets && fail(h, cudaMemcpyAsync(base + o_off, offsets, nb * 8, cudaMemcpyHostToDevice, s), "H2D offsets"))
+        return ACMPC_ERR_CUDA;
+    if (vmax && fail(h, cudaMemcpyAsync(base + o_vmax, vmax, nb * 8, cudaMemcpyHostToDevice, s), "H2D vmax"))
+        return ACMPC_ERR_CUDA;
+    acmpc_outputs d;
+    memset(&d, 0, sizeof(d));
+    if (out->controls) d.controls = reinterpret_cast<double*>(base + o_ctrl);
+    if (out->prediction) d.prediction = reinterpret_cast<double*>(base + o_pred);
+    if (out->cum_time) d.cum_time = reinterpret_cast<double*>(base + o_ct);
+    if (out->states) d.states = reinterpret_cast<double*>(base + o_st);
+    if (out->v_ref) d.v_ref = reinterpret_cast<double*>(base + o_vr);
+    if (out->cost) d.cost = reinterpret_cast<double*>(base + o_cost);
+    if (out->pri_res) d.pri_res = reinterpret_cast<double*>(base + o_pr);
+    if (out->dua_res) d.dua_res = reinterpret_cast<double*>(base + o_dr);
+    if (out->status) d.status = reinterpret_cast<int32_t*>(base + o_stat);
+    if (out->status_speed) d.status_speed = reinterpret_cast<int32_t*>(base + o_ss);
+    if (out->iters) d.iters = reinterpret_cast<int32_t*>(base + o_it);
+    if (out->rho_updates) d.rho_updates = reinterpret_cast<int32_t*>(base + o_ru);
+    if (out->waypoints) d.waypoints = reinterpret_cast<double*>(base + o_wp);
+    int rc = launch(h, B, reinterpret_cast<const double*>(base + o_paths),
+                    offsets ? reinterpret_cast<const double*>(base + o_off) : nullptr,
+                    vmax ? reinterpret_cast<const double*>(base + o_vmax) : nullptr, is_localised, &d, s);
+    if (rc != ACMPC_OK) return rc;
+#define ACMPC_D2H(field, bytes)                                                                              \
+    if (out->field &&                                                                                         \
+        fail(h, cudaMemcpyAsync(out->field, d.field, (bytes), cudaMemcpyDeviceToHost, s), "D2H " #field))     \
+        return ACMPC_ERR_CUDA;
+    ACMPC_D2H(controls, nb * 2 * n * 8)
+    ACMPC_D2H(prediction, nb * 2 * n * 8)
+    ACMPC_D2H(cum_time, nb * n * 8)
+    ACMPC_D2H(states, nb * 3 * H * 8)
+    ACMPC_D2H(v_ref, nb * n * 8)
+    ACMPC_D2H(cost, nb * 8)
+    ACMPC_D2H(pri_res, nb * 8)
+    ACMPC_D2H(dua_res, nb * 8)
+    ACMPC_D2H(status, nb * 4)
+    ACMPC_D2H(status_speed, nb * 4)
+    ACMPC_D2H(iters, nb * 8)
+    ACMPC_D2H(rho_updates, nb * 8)
+    ACMPC_D2H(waypoints, nb * 7 * n * 8)
+#undef ACMPC_D2H
+    if (fail(h, cudaStreamSynchronize(s), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
+    return ACMPC_OK;
+}
+
+int32_t acmpc_last_launch_info(const acmpc_handle* h, int32_t* n_launches, int32_t* smem_bytes,
+                               int32_t* threads_per_cta, int32_t* instances_per_cta)
+{
+    if (!h) return ACMPC_ERR_INVALID;
+    if (n_launches) *n_launches = h->last_launches;
+    if (smem_bytes) *smem_bytes = h->last_smem;
+    if (threads_per_cta) *threads_per_cta = h->last_threads;
+    if (instances_per_cta) *instances_per_cta = h->last_ipc;
+    return ACMPC_OK;
+}
+
+int32_t acmpc_fp64_peak_tflops(int32_t device, double* tflops)
+{
+    if (!tflops) return ACMPC_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return ACMPC_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return ACMPC_ERR_CUDA;
+    double* sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess) return ACMPC_ERR_CUDA;
+    const int iters = 1 << 14, threads = 256, blocks = prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(sink, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) {
+            cudaFree(sink);
+            return ACMPC_ERR_CUDA;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    cudaFree(sink);
+    const double flops = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return ACMPC_OK;
+}
+
+}  // extern "C"

@@ -1330,6 +1330,7 @@ struct ControlQP {
 struct InstanceOut {
     double *controls, *prediction, *cum_time, *states, *v_ref, *cost, *pri_res, *dua_res;
     int32_t *status, *status_speed, *iters, *rho_updates;
+    double* waypoints;
 };
 
 ACMPC_DEV void solve_instance(const Ctx& c, const double* raw_path, double offset, double v_max_live,
@@ -1370,6 +1371,8 @@ ACMPC_DEV void solve_instance(const Ctx& c, const double* raw_path, double offse
             }
             if (o.cum_time) o.cum_time[k] = tt;
             if (o.v_ref) o.v_ref[k] = vel[k];
+            if (o.waypoints)
+                for (int f = 0; f < 7; ++f) o.waypoints[f * n + k] = c.f(F_XS + f)[k];
         }
     }
     if (c.lane == 0) {

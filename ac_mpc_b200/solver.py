@@ -1,0 +1,201 @@
+"""Batched MPC step on one B200: host-side wrapper of the C ABI (include/acmpc_b200.h).
+
+`BatchedMPC` is the batched counterpart of the reference's `SpatialMPC.get_control`
+(/root/reference/src/acmpc/control/spatial_mpc.py:170-217): B independent instances per launch, one
+warp per instance.  PyTorch is used only to own device buffers and streams; numpy for host buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _capi
+
+
+def config_from_reference(control_config: dict, vehicle_data=None, **osqp_overrides) -> _capi.Config:
+    """Translate the dict `build_mpc` receives (controller.py:19-29) + the vehicle object
+    (`.vehicle_data.wheelbase`, `.vehicle_data.width`, `.max_steering_angle()`, dynamics.py:11-13)
+    into an `acmpc_config`."""
+    spc = control_config["speed_profile_constraints"]
+    cfg = _capi.default_config()
+    cfg.horizon = int(control_config["horizon"])
+    cfg.max_iter = int(control_config.get("max_iterations", 4000))   # MAX_SOLVER_ITERATIONS, spatial_mpc.py:17
+    cfg.v_min, cfg.v_max = float(spc["v_min"]), float(spc["v_max"])
+    cfg.a_min, cfg.a_max = float(spc["a_min"]), float(spc["a_max"])
+    cfg.ay_max, cfg.ki_min = float(spc["ay_max"]), float(spc["ki_min"])
+    end_v = spc.get("end_velocity")
+    cfg.has_end_velocity = 0 if end_v is None else 1
+    cfg.end_velocity = 0.0 if end_v is None else float(end_v)
+    _capi.apply_overrides(cfg, dict(step_cost=control_config["step_cost"], r_term=control_config["r_term"],
+                                    final_cost=control_config["final_cost"]))
+    if vehicle_data is not None:
+        cfg.wheelbase = float(vehicle_data.vehicle_data.wheelbase)
+        cfg.width = float(vehicle_data.vehicle_data.width)
+        cfg.delta_max = float(vehicle_data.max_steering_angle())
+    # build-time limits of SpatialBicycleModel (controller.py:20-24): frozen here, like the reference
+    cfg.input_v_min, cfg.input_v_max = float(spc["v_min"]), float(spc["v_max"])
+    _capi.apply_overrides(cfg, osqp_overrides)
+    return cfg
+
+
+class BatchedMPC:
+    """Owns one `acmpc_handle`.  The handle (and the CUDA context) is created lazily on first use so
+    an object constructed before a fork (controller.py:293-297) initialises CUDA in the child."""
+
+    def __init__(self, cfg: _capi.Config, device: int = 0):
+        self.cfg = cfg
+        self.device = int(device)
+        self.H = int(cfg.horizon)
+        self.n = self.H - 1
+        self._h = None
+        self._lib = _capi.load()
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def _handle(self):
+        if self._h is None:
+            h = C.c_void_p()
+            rc = self._lib.acmpc_create(C.byref(self.cfg), self.device, C.byref(h))
+            if rc != 0:
+                raise RuntimeError(
+                    f"acmpc_create failed: {_capi.RC_NAMES.get(rc, rc)} "
+                    "(the MPC step is CUDA-only; a B200 (sm_100) device is required, there is no CPU fallback)")
+            self._h = h
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            self._lib.acmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.acmpc_last_error(self._h).decode() if self._h else ""
+            raise RuntimeError(f"acmpc call failed: {_capi.RC_NAMES.get(rc, rc)} {msg}")
+
+    def launch_info(self) -> Dict[str, int]:
+        vals = [C.c_int32() for _ in range(4)]
+        self._check(self._lib.acmpc_last_launch_info(self._handle(), *[C.byref(v) for v in vals]))
+        return dict(zip(("launches", "smem_bytes", "threads_per_cta", "instances_per_cta"), (v.value for v in vals)))
+
+    # -- host buffers ---------------------------------------------------------------------------
+    def alloc_host_outputs(self, B: int, fields=None, pinned: bool = False):
+        """numpy arrays (optionally views of pinned torch tensors) for every requested field."""
+        spec = _capi.output_spec(self.H)
+        fields = list(spec) if fields is None else list(fields)
+        arrs = {}
+        keep = []
+        for name in fields:
+            shp, dt = spec[name]
+            if pinned:
+                import torch
+
+                t = torch.empty((B,) + shp, dtype=getattr(torch, dt)).pin_memory()
+                keep.append(t)
+                arrs[name] = t.numpy()
+            else:
+                arrs[name] = np.empty((B,) + shp, dtype=dt)
+        arrs["_keepalive"] = keep
+        return arrs
+
+    def solve_host(self, paths, offsets=None, vmax=None, is_localised: bool = False, out=None, fields=None):
+        """HOST buffers in, HOST buffers out (acmpc_solve_batch_host): H2D + kernel + D2H + sync."""
+        paths = np.ascontiguousarray(paths, dtype=np.float64)
+        if paths.ndim != 3 or paths.shape[1:] != (self.H, 3):
+            raise ValueError(f"paths must be (B, {self.H}, 3), got {paths.shape}")
+        B = paths.shape[0]
+        offsets = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.float64)
+        vmax = None if vmax is None else np.ascontiguousarray(vmax, dtype=np.float64)
+        for a, nm in ((offsets, "offsets"), (vmax, "vmax")):
+            if a is not None and a.shape != (B,):
+                raise ValueError(f"{nm} must have shape ({B},)")
+        if out is None:
+            out = self.alloc_host_outputs(B, fields)
+        o = _capi.Outputs()
+        for name in _capi.OUTPUT_FIELDS:
+            if name in out:
+                setattr(o, name, out[name].ctypes.data)
+        dp = C.POINTER(C.c_double)
+        ptr = lambda a: a.ctypes.data_as(dp) if a is not None else None
+        self._check(self._lib.acmpc_solve_batch_host(self._handle(), B, ptr(paths), ptr(offsets), ptr(vmax),
+                                                     int(bool(is_localised)), 0, C.byref(o)))
+        return out
+
+    # -- device buffers -------------------------------------------------------------------------
+    def alloc_device_outputs(self, B: int, fields=None):
+        """One packed uint8 CUDA tensor with a 256-byte aligned slab per field (so a multi-GPU run
+        gathers ONE buffer), plus typed views.  Returns (packed, views)."""
+        import torch
+
+        spec = _capi.output_spec(self.H)
+        fields = list(spec) if fields is None else list(fields)
+        offs, total = {}, 0
+        for name in fields:
+            shp, dt = spec[name]
+            nbytes = B * int(np.prod(shp, dtype=np.int64)) * np.dtype(dt).itemsize
+            offs[name] = (total, nbytes)
+            total = (total + nbytes + 255) // 256 * 256
+        packed = torch.empty(max(total, 256), dtype=torch.uint8, device=f"cuda:{self.device}")
+        views = {}
+        for name in fields:
+            shp, dt = spec[name]
+            o, nb = offs[name]
+            views[name] = packed[o:o + nb].view(getattr(torch, dt)).view((B,) + shp)
+        return packed, views
+
+    @staticmethod
+    def unpack(packed, B: int, H: int, fields=None):
+        """Typed views of a packed output buffer (same layout as alloc_device_outputs)."""
+        import torch
+
+        spec = _capi.output_spec(H)
+        fields = list(spec) if fields is None else list(fields)
+        views, total = {}, 0
+        for name in fields:
+            shp, dt = spec[name]
+            nbytes = B * int(np.prod(shp, dtype=np.int64)) * np.dtype(dt).itemsize
+            views[name] = packed[total:total + nbytes].view(getattr(torch, dt)).view((B,) + shp)
+            total = (total + nbytes + 255) // 256 * 256
+        return views
+
+    def solve_device(self, paths, offsets=None, vmax=None, is_localised: bool = False, out=None, stream=None):
+        """DEVICE tensors in/out (acmpc_solve_batch_device); asynchronous on `stream` (torch stream or
+        None = torch's current stream).  `out` = dict of CUDA tensors from alloc_device_outputs."""
+        import torch
+
+        if not (paths.is_cuda and paths.dtype == torch.float64 and paths.is_contiguous()):
+            raise ValueError("paths must be a contiguous float64 CUDA tensor")
+        if paths.dim() != 3 or tuple(paths.shape[1:]) != (self.H, 3):
+            raise ValueError(f"paths must be (B, {self.H}, 3)")
+        B = paths.shape[0]
+        for a in (offsets, vmax):
+            if a is not None and not (a.is_cuda and a.dtype == torch.float64 and a.is_contiguous() and a.numel() == B):
+                raise ValueError("offsets / vmax must be contiguous float64 CUDA tensors of B elements")
+        if out is None:
+            _, out = self.alloc_device_outputs(B)
+        o = _capi.Outputs()
+        for name in _capi.OUTPUT_FIELDS:
+            if name in out:
+                setattr(o, name, out[name].data_ptr())
+        s = torch.cuda.current_stream(paths.device) if stream is None else stream
+        self._check(self._lib.acmpc_solve_batch_device(
+            self._handle(), B, paths.data_ptr(), None if offsets is None else offsets.data_ptr(),
+            None if vmax is None else vmax.data_ptr(), int(bool(is_localised)), None, 0, C.byref(o),
+            C.c_void_p(s.cuda_stream)))
+        return out
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    """Measured FP64 FMA throughput of the device (roofline denominator of this path)."""
+    v = C.c_double()
+    rc = _capi.load().acmpc_fp64_peak_tflops(int(device), C.byref(v))
+    if rc != 0:
+        raise RuntimeError(f"acmpc_fp64_peak_tflops failed: {_capi.RC_NAMES.get(rc, rc)}")
+    return v.value

@@ -86,6 +86,7 @@ typedef struct acmpc_outputs {
     int32_t *status_speed;  /* [B]     speed-profile QP status */
     int32_t *iters;         /* [B,2]   ADMM iterations: speed QP, control QP */
     int32_t *rho_updates;   /* [B,2]   refactorisations caused by adaptive rho */
+    double *waypoints;      /* [B,7,n] ReferencePath rows xs ys psis kappas distances widths velocities  reference_path */
 } acmpc_outputs;
 
 typedef struct acmpc_handle acmpc_handle;

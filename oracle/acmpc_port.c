@@ -321,6 +321,7 @@ int acmpc_port_step(acmpc_port *p, const double *path, double offset, double v_m
         for (int k = 0; k < n; k++) o->cum_time[k] = x[3 * k + 2];
     if (o->states) memcpy(o->states, x, sizeof(double) * (size_t)(3 * H));
     if (o->v_ref) memcpy(o->v_ref, vel, sizeof(double) * (size_t)n);
+    if (o->waypoints) memcpy(o->waypoints, wp, sizeof(double) * (size_t)(7 * n));
     if (o->cost) *o->cost = ci.obj_val;
     if (o->pri_res) *o->pri_res = ci.pri_res;
     if (o->dua_res) *o->dua_res = ci.dua_res;
@@ -389,6 +390,7 @@ static void *batch_worker(void *arg)
             if (out->status_speed) o.status_speed = out->status_speed + b;
             if (out->iters) o.iters = out->iters + (size_t)b * 2;
             if (out->rho_updates) o.rho_updates = out->rho_updates + (size_t)b * 2;
+            if (out->waypoints) o.waypoints = out->waypoints + (size_t)b * 7 * n;
             acmpc_port_step(p, j->paths + (size_t)b * 3 * H, j->offsets ? j->offsets[b] : 0.0,
                             j->vmax ? j->vmax[b] : j->cfg->v_max, j->is_localised, 0, &o);
         }

@@ -95,6 +95,7 @@ class Outputs(C.Structure):
         ("states", C.c_void_p), ("v_ref", C.c_void_p), ("cost", C.c_void_p),
         ("pri_res", C.c_void_p), ("dua_res", C.c_void_p), ("status", C.c_void_p),
         ("status_speed", C.c_void_p), ("iters", C.c_void_p), ("rho_updates", C.c_void_p),
+        ("waypoints", C.c_void_p),
     ]
 
 
@@ -250,6 +251,7 @@ OUTPUT_SPEC = {
     "status_speed": (lambda H, n: (), np.int32),
     "iters": (lambda H, n: (2,), np.int32),
     "rho_updates": (lambda H, n: (2,), np.int32),
+    "waypoints": (lambda H, n: (7, n), np.float64),
 }
 
 

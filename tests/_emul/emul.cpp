@@ -38,6 +38,7 @@ extern "C" int acmpc_emul_solve_batch(const acmpc_config* cfg, int B, const doub
         o.status_speed = out->status_speed ? out->status_speed + b : nullptr;
         o.iters = out->iters ? out->iters + (size_t)b * 2 : nullptr;
         o.rho_updates = out->rho_updates ? out->rho_updates + (size_t)b * 2 : nullptr;
+        o.waypoints = out->waypoints ? out->waypoints + (size_t)b * 7 * n : nullptr;
         acmpc::solve_instance(c, raw, offsets ? offsets[b] : 0.0, vmax ? vmax[b] : cfg->v_max,
                               is_localised, o);
     }
