@@ -181,6 +181,15 @@ ACMPC_DEV double rho_estimate(const Norms& N, double rho)
     return clampd(r, kRhoMin, kRhoMax);
 }
 
+// OSQP overwrites info.obj_val when a certificate fires (check_termination): +-OSQP_INFTY, NaN if non-convex
+ACMPC_DEV double final_obj(int status, double obj)
+{
+    if (status == ACMPC_PRIMAL_INFEASIBLE || status == ACMPC_PRIMAL_INFEASIBLE_INACCURATE) return kInfty;
+    if (status == ACMPC_DUAL_INFEASIBLE || status == ACMPC_DUAL_INFEASIBLE_INACCURATE) return -kInfty;
+    if (status == ACMPC_NON_CVX) return NAN;
+    return obj;
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-QP context
 // ------------------------------------------------------------------------------------------------
@@ -631,7 +640,7 @@ struct SpeedQP {
             obj += 0.5 * P[i] * X[i] * X[i] + Q[i] * X[i];
             Rv[i] = X[i] / DI[i];
         }
-        info.obj_val = warp_sum(obj) * cinv;
+        info.obj_val = final_obj(status, warp_sum(obj) * cinv);
         ACMPC_SYNC();
     }
 };
@@ -1319,7 +1328,7 @@ struct ControlQP {
                 obj += 0.5 * c.f(C_P + j)[k] * x * x;
                 if (j >= 3) obj += c.f(C_Q + j - 3)[k] * x;
             }
-        info.obj_val = warp_sum(obj) * cinv;
+        info.obj_val = final_obj(status, warp_sum(obj) * cinv);
     }
 };
 
