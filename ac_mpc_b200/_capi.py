@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libacmpc_b200.so")
-_SOURCES = [os.path.join(CSRC, "acmpc_b200.cu"), os.path.join(CSRC, "mpc_body.cuh"),
+_SOURCES = [os.path.join(CSRC, "acmpc_b200.cu"), os.path.join(CSRC, "mpc_warp.cuh"), os.path.join(CSRC, "simt.cuh"),
             os.path.join(os.path.dirname(_HERE), "include", "acmpc_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

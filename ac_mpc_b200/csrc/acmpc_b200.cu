@@ -2,8 +2,9 @@
 //
 // One warp (one CTA of 32 threads) owns one problem instance; its (H,3) reference-path slice is
 // staged into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier), everything else
-// (waypoints, both QPs, ADMM iterates, factorisations) stays in that CTA's shared memory until the
-// results are written back.  The per-instance algorithm is in mpc_body.cuh.
+// (waypoints, both QPs, ADMM iterates, factorisations) stays in that CTA's registers and shared memory
+// until the results are written back.  The per-instance algorithm is in mpc_warp.cuh; the kernel is
+// instantiated for C = ceil(H/32) = 1..4 horizon stages per lane.
 //
 // There is NO CPU path in this library: acmpc_create fails with ACMPC_ERR_NO_DEVICE without a GPU.
 #include <cuda_runtime.h>
@@ -14,7 +15,7 @@
 #include <new>
 #include <string>
 
-#include "mpc_body.cuh"
+#include "mpc_warp.cuh"
 
 namespace {
 
@@ -27,7 +28,6 @@ struct KernelParams {
     int32_t B;
     int32_t is_localised;
     int32_t use_tma;
-    int32_t qp_doubles;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -63,18 +63,19 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
     }
 }
 
+template <int C>
 __global__ void __launch_bounds__(32) acmpc_step_kernel(const __grid_constant__ KernelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int b = blockIdx.x;
     const int lane = threadIdx.x;
     const int H = p.cfg.horizon, n = H - 1;
-    acmpc::Ctx c;
+    acmpc::Ctx<C> c;
     c.S = reinterpret_cast<double*>(smem_raw);
-    c.H = H, c.n = n, c.Hs = H, c.lane = lane, c.cfg = &p.cfg;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(c.S + p.qp_doubles);
-    // the raw path slice lands at the start of the QP region: it is dead before the QP data is built
-    double* raw = c.f(acmpc::F_PATH_END);
+    c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(c.S + acmpc::Layout<C>::kDoubles);
+    // the raw path slice lands in the scan-matrix region: it is dead before the first control factorisation
+    double* raw = c.scan(0, 0);
     const double* src = p.paths + (size_t)b * 3 * H;
     if (p.use_tma) {
         tma_load_1d(raw, src, (uint32_t)(3 * H * sizeof(double)), mbar, lane);
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(32) acmpc_step_kernel(const __grid_constant__ 
     o.waypoints = g.waypoints ? g.waypoints + (size_t)b * 7 * n : nullptr;
     const double offset = p.offsets ? p.offsets[b] : 0.0;
     const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
-    acmpc::solve_instance(c, raw, offset, vmax, p.is_localised, o);
+    acmpc::solve_instance<C>(c, raw, offset, vmax, p.is_localised, o);
 }
 
 // FP64 FMA throughput probe: 8 independent chains per thread, no memory traffic.
@@ -162,7 +163,29 @@ bool valid_config(const acmpc_config* c, std::string* why)
     return true;
 }
 
-size_t smem_bytes_for(int H) { return sizeof(double) * (size_t)acmpc::kFieldsPerStage * H + 16; }
+int stages_per_lane(int H) { return (H + 31) / 32; }
+
+size_t smem_bytes_for(int H)
+{
+    size_t d = 0;
+    switch (stages_per_lane(H)) {
+        case 1: d = acmpc::smem_doubles<1>(); break;
+        case 2: d = acmpc::smem_doubles<2>(); break;
+        case 3: d = acmpc::smem_doubles<3>(); break;
+        default: d = acmpc::smem_doubles<4>(); break;
+    }
+    return sizeof(double) * d + 16;
+}
+
+const void* kernel_for(int H)
+{
+    switch (stages_per_lane(H)) {
+        case 1: return reinterpret_cast<const void*>(&acmpc_step_kernel<1>);
+        case 2: return reinterpret_cast<const void*>(&acmpc_step_kernel<2>);
+        case 3: return reinterpret_cast<const void*>(&acmpc_step_kernel<3>);
+        default: return reinterpret_cast<const void*>(&acmpc_step_kernel<4>);
+    }
+}
 
 int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offsets, const double* d_vmax,
            int is_localised, const acmpc_outputs* d_out, cudaStream_t stream)
@@ -174,11 +197,12 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     p.out = *d_out;
     p.B = B, p.is_localised = is_localised ? 1 : 0;
     const int H = h->cfg.horizon;
-    p.qp_doubles = acmpc::kFieldsPerStage * H;
     // TMA bulk copies need 16-byte aligned ends and a size that is a multiple of 16
     p.use_tma = ((3 * H * sizeof(double)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_paths) & 15) == 0);
     const size_t smem = smem_bytes_for(H);
-    acmpc_step_kernel<<<B, 32, smem, stream>>>(p);
+    void* args[] = {&p};
+    if (fail(h, cudaLaunchKernel(kernel_for(H), dim3(B), dim3(32), args, smem, stream), "kernel launch"))
+        return ACMPC_ERR_CUDA;
     h->last_launches = 1, h->last_smem = (int)smem, h->last_threads = 32, h->last_ipc = 1;
     if (fail(h, cudaGetLastError(), "kernel launch")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
@@ -237,7 +261,7 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
     h->sm_count = prop.multiProcessorCount;
     const size_t smem = smem_bytes_for(cfg->horizon);
     if (smem > (size_t)prop.sharedMemPerBlockOptin ||
-        fail(h, cudaFuncSetAttribute(acmpc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        fail(h, cudaFuncSetAttribute(kernel_for(cfg->horizon), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
              "cudaFuncSetAttribute") ||
         fail(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
         delete h;

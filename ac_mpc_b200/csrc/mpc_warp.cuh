@@ -1,0 +1,1439 @@
+// mpc_warp.cuh -- one warp solves one MPC step (SpatialMPC.get_control), warp-parallel over the horizon.
+//
+// Reference path being replaced (file:line under /root/reference/src/acmpc/control/):
+//   spatial_mpc.py:125-154   construct_waypoints          -> build_waypoints()
+//   solvers/speed_profile.py:26-59,131-150 + osqp        -> SpeedQP
+//   dynamics.py:23-40 (t2s), :65-103 (linearise)          -> ControlQP::setup()
+//   solvers/control.py:26-79,121-158 + osqp               -> ControlQP
+//   spatial_mpc.py:193-212, dynamics.py:42-63 (s2t)       -> solve_instance() tail
+//
+// Execution model (revision r1b):
+//   * lane l owns the C = ceil(H/32) CONTIGUOUS horizon stages C*l .. C*l+C-1; C is a template
+//     parameter so that all per-stage state is register arrays.
+//   * stage s owns  x_s = (e_y, e_psi, t),  u_{s-1} = (v, kappa_cmd),  the equality block
+//     "m*x_s + A_{s-1} x_{s-1} + B_{s-1} u_{s-1} = b_s", the bound rows of x_s and u_{s-1}, the entries of
+//     A_s (columns of x_s in block s+1) and of B_{s-1}.  With this ownership one ADMM iteration
+//     exchanges only two 3-vectors between neighbouring stages (register shuffles).
+//   * the ADMM iterates (x, z, y) stay in REGISTERS for the whole solve; the scaled problem data and the
+//     factorisation live in shared memory, one conflict-free column per lane.
+//   * OSQP's linear system is solved in reduced form  (P + sigma I + A' diag(rho) A) x~ = rhs:  the inputs
+//     are eliminated analytically, the remaining SPD block-tridiagonal system (3x3 blocks) is factorised
+//     once per rho (block LDL') and each solve is two warp-parallel affine scans (Kogge-Stone over lanes
+//     with precomputed 3x3 prefix products; the backward scan reads the transposed forward matrices).
+//   * the speed-profile QP is the scalar version of the same scheme and lives entirely in registers.
+// Everything else (Ruiz equilibration, rho classes, relaxation, projection, dual update, unscaled
+// residuals, infeasibility certificates, adaptive rho) follows OSQP 0.6.x step for step, because the
+// reference's answer is defined by OSQP's iterate at its termination check.
+//
+// The same source is compiled (a) by nvcc for sm_100a into the product library and (b) by g++ with
+// -DACMPC_EMULATE into tests/_emul (a 32-lane lock-step emulation, TEST ONLY, see simt.cuh).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/acmpc_b200.h"
+#include "simt.cuh"
+
+namespace acmpc {
+
+constexpr double kInfty = 1e30;
+constexpr double kMinScaling = 1e-4;
+constexpr double kMaxScaling = 1e4;
+constexpr double kRhoMin = 1e-6;
+constexpr double kRhoMax = 1e6;
+constexpr double kRhoEqOverIneq = 1e3;
+constexpr double kRhoTol = 1e-4;
+constexpr double kBig = kInfty * kMinScaling;   // "infinite bound" threshold in scaled space
+constexpr double kPi = 3.14159265358979323846;
+constexpr int kLevels = 5;                      // Kogge-Stone levels over 32 lanes
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory map.  Per-stage field f of stage (lane, j) is S[(f*C + j)*32 + lane].
+// ------------------------------------------------------------------------------------------------
+enum : int {
+    F_XS = 0, F_YS, F_PSI, F_VEL,   // ReferencePath rows needed after the solves (paths.py:4-72)
+    K_M,                            // 3: coefficient of x_s in its own equality block (raw -1)
+    K_A = K_M + 3,                  // 6: a11 a12 a21 a22 a31 a33 of A_s (rows of block s+1)
+    K_B = K_A + 6,                  // 2: b22 b31 of B_{s-1} (rows of block s)
+    K_S = K_B + 2,                  // 5: bound ("identity") rows
+    K_Q = K_S + 5,                  // 2: q of (v, kappa_cmd); the state part of q is exactly zero
+    K_IV = K_Q + 2, K_IK,           // 1/K_uu of the two inputs
+    K_RB31, K_RB22,                 // rho_eq * b31, rho_eq * b22
+    K_BE,                           // 3: scaled equality right-hand side (l == u)
+    K_LB = K_BE + 3,                // 5
+    K_UB = K_LB + 5,                // 5
+    K_RHO = K_UB + 5,               // 5: rho of the bound rows (by class; rewritten with every rho update)
+    K_RINV = K_RHO + 5,             // 5: 1/rho of the bound rows
+    K_P = K_RINV + 5,               // 5: diagonal of P            (termination checks only)
+    K_DI = K_P + 5,                 // 5: 1/D                      (termination checks, outputs)
+    K_EEI = K_DI + 5,               // 3: 1/E of the equality block (termination checks only)
+    K_EBI = K_EEI + 3,              // 5: 1/E of the bound rows     (termination checks only)
+    K_N = K_EBI + 5,                // 9: N_s = -S_{s,s-1} Sigma_{s-1}^{-1}   (row major)
+    K_SI = K_N + 9,                 // 6: Sigma_s^{-1}  (00 10 11 20 21 22)
+    K_FIELDS = K_SI + 6
+};
+
+template <int C>
+struct Layout {
+    static constexpr int kDoubles = (K_FIELDS * C + kLevels * 9) * 32;
+};
+template <int C>
+constexpr int smem_doubles()
+{
+    return Layout<C>::kDoubles;
+}
+
+AC_DEV double limit_scaling_u(double v)
+{
+    v = v < kMinScaling ? 1.0 : v;
+    return v > kMaxScaling ? kMaxScaling : v;
+}
+AC_DEV VD limit_scaling(const VD& v)
+{
+    VD t = vsel(v < VD(kMinScaling), VD(1.0), v);
+    return vsel(t > VD(kMaxScaling), VD(kMaxScaling), t);
+}
+AC_DEV double clampu(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+AC_DEV VD vclamp(const VD& v, const VD& lo, const VD& hi) { return vsel(v < lo, lo, vsel(v > hi, hi, v)); }
+AC_DEV VD inv_sqrt(const VD& v) { return vrsqrt(v); }
+
+// numpy's mod for a positive modulus
+AC_DEV VD np_mod(const VD& a, double b)
+{
+    VD r = vfmod(a, b);
+    return vsel(r < VD(0.0), r + VD(b), r);
+}
+AC_DEV double np_mod_u(double a, double b)
+{
+    double r = fmod(a, b);
+    return r < 0.0 ? r + b : r;
+}
+
+// OSQP constraint classes (set_rho_vec): 0 inequality, 1 equality, 2 loose
+AC_DEV VI row_class(const VD& l, const VD& u)
+{
+    VB loose = (l < VD(-kBig)) & (u > VD(kBig));
+    VB eq = (u - l) < VD(kRhoTol);
+    return vseli(loose, vi_all(2), vseli(eq, vi_all(1), vi_all(0)));
+}
+
+struct RhoSet {
+    double rho, rho_eq, rinv, rinv_eq;
+    AC_MEM void set(double r)
+    {
+        rho = r;
+        rho_eq = kRhoEqOverIneq * r;
+        rinv = 1.0 / rho;
+        rinv_eq = 1.0 / rho_eq;
+    }
+    AC_MEM VD of(const VI& cls, int sh) const
+    {
+        return vsel(vi_field_is(cls, sh, 0), VD(rho), vsel(vi_field_is(cls, sh, 1), VD(rho_eq), VD(kRhoMin)));
+    }
+    AC_MEM VD inv_of(const VI& cls, int sh) const
+    {
+        return vsel(vi_field_is(cls, sh, 0), VD(rinv), vsel(vi_field_is(cls, sh, 1), VD(rinv_eq), VD(1.0 / kRhoMin)));
+    }
+};
+
+// norms gathered at a termination check (update_info + compute_*_tol + compute_rho_estimate)
+struct Norms {
+    double pri, dua, nz, nAx, nq, nAty, nPx;               // unscaled (termination)
+    double s_pri, s_dua, s_z, s_Ax, s_q, s_Aty, s_Px;      // scaled (rho estimate)
+};
+
+struct SolveInfo {
+    int status, iter, rho_updates;
+    double pri_res, dua_res, obj_val;
+};
+
+AC_DEV double rho_estimate(const Norms& N, double rho)
+{
+    double p = N.s_pri / (fmax(N.s_z, N.s_Ax) + 1e-10);
+    double d = N.s_dua / (fmax(N.s_q, fmax(N.s_Aty, N.s_Px)) + 1e-10);
+    double r = rho * sqrt(p / (d + 1e-10));
+    return clampu(r, kRhoMin, kRhoMax);
+}
+
+// OSQP overwrites info.obj_val when a certificate fires (check_termination): +-OSQP_INFTY, NaN if non-convex
+AC_DEV double final_obj(int status, double obj)
+{
+    if (status == ACMPC_PRIMAL_INFEASIBLE || status == ACMPC_PRIMAL_INFEASIBLE_INACCURATE) return kInfty;
+    if (status == ACMPC_DUAL_INFEASIBLE || status == ACMPC_DUAL_INFEASIBLE_INACCURATE) return -kInfty;
+    if (status == ACMPC_NON_CVX) return NAN;
+    return obj;
+}
+
+// the 12 max-norms of one termination check -> Norms
+AC_DEV void finish_norms(VD (&v)[12], double cinv, double nq_unscaled, double nq_scaled, Norms& N)
+{
+    double m[12];
+    for (int t = 0; t < 12; ++t) m[t] = wmax(v[t]);
+    N.pri = m[0], N.nz = m[1], N.nAx = m[2];
+    N.dua = cinv * m[3], N.nAty = m[4], N.nPx = m[5], N.nq = nq_unscaled;
+    N.s_dua = m[6], N.s_pri = m[7], N.s_z = m[8], N.s_Ax = m[9], N.s_Aty = m[10], N.s_Px = m[11];
+    N.s_q = nq_scaled;
+}
+AC_DEV void acc_row(VD (&v)[12], const VD& ax, const VD& z, const VD& einv)
+{
+    VD res = ax - z;
+    v[0] = vmax(v[0], vabs(einv * res)), v[7] = vmax(v[7], vabs(res));
+    v[1] = vmax(v[1], vabs(einv * z)), v[8] = vmax(v[8], vabs(z));
+    v[2] = vmax(v[2], vabs(einv * ax)), v[9] = vmax(v[9], vabs(ax));
+}
+AC_DEV void acc_col(VD (&v)[12], const VD& q, const VD& px, const VD& aty, const VD& dinv)
+{
+    VD dr = q + px + aty;
+    v[3] = vmax(v[3], vabs(dinv * dr)), v[6] = vmax(v[6], vabs(dr));
+    v[4] = vmax(v[4], vabs(dinv * aty)), v[10] = vmax(v[10], vabs(aty));
+    v[5] = vmax(v[5], vabs(dinv * px)), v[11] = vmax(v[11], vabs(px));
+}
+// is_primal_infeasible's projection of delta_y by bound type
+AC_DEV VD project_dy(const VD& dy, const VD& lo, const VD& hi)
+{
+    VB up_inf = hi > VD(kBig), lo_inf = lo < VD(-kBig);
+    VD a = vsel(lo_inf, VD(0.0), vmin(dy, VD(0.0)));   // upper infinite
+    VD b = vsel(lo_inf, vmax(dy, VD(0.0)), dy);        // upper finite
+    return vsel(up_inf, a, b);
+}
+AC_DEV VD support(const VD& dy, const VD& lo, const VD& hi)
+{
+    return hi * vmax(dy, VD(0.0)) + lo * vmin(dy, VD(0.0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-instance context
+// ------------------------------------------------------------------------------------------------
+template <int C>
+struct Ctx {
+    double* S;   // base of this instance's shared-memory block
+    int H, n;
+    const acmpc_config* cfg;
+    VI lane;
+    AC_MEM double* col(int f, int j) const { return S + (f * C + j) * 32; }
+    AC_MEM VD ld(int f, int j) const { return ld_lane(col(f, j)); }
+    AC_MEM void st(int f, int j, const VD& v) const { st_lane(col(f, j), v); }
+    AC_MEM double* scan(int lvl, int e) const { return S + (K_FIELDS * C + lvl * 9 + e) * 32; }
+    AC_MEM VI stage(int j) const { return lane * C + j; }
+};
+
+// value held by the NEXT stage (s+1) for every own stage; 0 beyond lane 31
+template <int C>
+AC_DEV void pull_next(const VD (&v)[C], VD (&o)[C])
+{
+    VD nx = shfl_down0(v[0], 1);
+    AC_UNROLL
+    for (int j = 0; j + 1 < C; ++j) o[j] = v[j + 1];
+    o[C - 1] = nx;
+}
+// value held by the PREVIOUS stage (s-1); 0 before lane 0
+template <int C>
+AC_DEV void pull_prev(const VD (&v)[C], VD (&o)[C])
+{
+    VD pv = shfl_up0(v[C - 1], 1);
+    AC_UNROLL
+    for (int j = C - 1; j >= 1; --j) o[j] = v[j - 1];
+    o[0] = pv;
+}
+template <int C, int K>
+AC_DEV void pull_next_k(const VD (&v)[C][K], VD (&o)[C][K])
+{
+    AC_UNROLL
+    for (int e = 0; e < K; ++e) {
+        VD nx = shfl_down0(v[0][e], 1);
+        AC_UNROLL
+        for (int j = 0; j + 1 < C; ++j) o[j][e] = v[j + 1][e];
+        o[C - 1][e] = nx;
+    }
+}
+template <int C, int K>
+AC_DEV void pull_prev_k(const VD (&v)[C][K], VD (&o)[C][K])
+{
+    AC_UNROLL
+    for (int e = 0; e < K; ++e) {
+        VD pv = shfl_up0(v[C - 1][e], 1);
+        AC_UNROLL
+        for (int j = C - 1; j >= 1; --j) o[j][e] = v[j - 1][e];
+        o[0][e] = pv;
+    }
+}
+
+// hot-loop variants without the out-of-range select: the consumer multiplies what lane 31 "pulls" by the
+// (zero) A of its last stage; lane 0 pulls the (zero) A-product of lane 31's last stage by rotation.
+template <int C, int K>
+AC_DEV void pull_next_raw(const VD (&v)[C][K], VD (&o)[C][K])
+{
+    AC_UNROLL
+    for (int e = 0; e < K; ++e) {
+        VD nx = shfl_down_raw(v[0][e], 1);
+        AC_UNROLL
+        for (int j = 0; j + 1 < C; ++j) o[j][e] = v[j + 1][e];
+        o[C - 1][e] = nx;
+    }
+}
+template <int C, int K>
+AC_DEV void pull_prev_rot(const VD (&v)[C][K], VD (&o)[C][K])
+{
+    AC_UNROLL
+    for (int e = 0; e < K; ++e) {
+        VD pv = shfl_rot_up1(v[C - 1][e]);
+        AC_UNROLL
+        for (int j = C - 1; j >= 1; --j) o[j][e] = v[j - 1][e];
+        o[0][e] = pv;
+    }
+}
+
+// o += M v  /  o += M' v   (M row major 3x3)
+AC_DEV void mv_acc(const VD (&M)[9], const VD (&v)[3], VD (&o)[3])
+{
+    o[0] = o[0] + (M[0] * v[0] + M[1] * v[1] + M[2] * v[2]);
+    o[1] = o[1] + (M[3] * v[0] + M[4] * v[1] + M[5] * v[2]);
+    o[2] = o[2] + (M[6] * v[0] + M[7] * v[1] + M[8] * v[2]);
+}
+AC_DEV void mtv_acc(const VD (&M)[9], const VD (&v)[3], VD (&o)[3])
+{
+    o[0] = o[0] + (M[0] * v[0] + M[3] * v[1] + M[6] * v[2]);
+    o[1] = o[1] + (M[1] * v[0] + M[4] * v[1] + M[7] * v[2]);
+    o[2] = o[2] + (M[2] * v[0] + M[5] * v[1] + M[8] * v[2]);
+}
+
+// ReferencePath rows of the lane's stages, in registers while the QPs are assembled
+template <int C>
+struct PathRegs {
+    VD xs[C], ys[C], psi[C], kap[C], dist[C], wid[C];
+};
+
+// spatial_mpc.py:125-154.  `W` = raw (H,3) path staged in shared memory.
+template <int C>
+AC_DEV void build_waypoints(const Ctx<C>& c, const double* W, PathRegs<C>& p)
+{
+    const int n = c.n, H = c.H;
+    AC_UNROLL
+    for (int j = 0; j < C; ++j) {
+        VI s = c.stage(j);
+        VB ok = vi_lt(s, n);
+        VI ic = s * 3, in = ic + 3;
+        VI ip = vseli(vi_eq(s, 0), vi_all(3 * (H - 1)), ic + (-3));
+        VD cx = ld_idx_if(ok, W, ic, 0.0), cy = ld_idx_if(ok, W, ic + 1, 0.0);
+        VD nx = ld_idx_if(ok, W, in, 0.0), ny = ld_idx_if(ok, W, in + 1, 0.0), nw = ld_idx_if(ok, W, in + 2, 0.0);
+        VD px = ld_idx_if(ok, W, ip, 0.0), py = ld_idx_if(ok, W, ip + 1, 0.0);
+        VD ax = nx - cx, ay = ny - cy, bx = cx - px, by = cy - py;
+        VD ps = vatan2(ay, ax);
+        VD d = vsqrt(ax * ax + ay * ay);
+        VD behind = vatan2(by, bx);
+        VD dang = np_mod(ps - behind + VD(kPi), 2.0 * kPi) - VD(kPi);
+        p.xs[j] = cx, p.ys[j] = cy, p.wid[j] = nw;
+        p.psi[j] = vsel(ok, ps, VD(0.0));
+        p.dist[j] = vsel(ok, d, VD(0.0));
+        p.kap[j] = vsel(ok, dang / (d + VD(1e-12)) + VD(1e-12), VD(0.0));
+    }
+    // kappa_0 := kappa_1
+    VD kn[C];
+    pull_next<C>(p.kap, kn);
+    p.kap[0] = vsel(vi_eq(c.stage(0), 0), kn[0], p.kap[0]);
+}
+
+// ================================================================================================
+// Speed-profile QP   min 1/2 v'v - vbar'v   s.t.  a_min <= (v_{i+1}-v_i)/(2 d_i) <= a_max,
+//                                                  v_min <= v_i <= vbar_i          (speed_profile.py)
+// Stage i owns v_i, its bound row and acceleration row i (i <= n-2).  All state in registers.
+// ================================================================================================
+template <int C>
+struct SpeedQP {
+    const Ctx<C>& c;
+    int n;
+    VD al[C], au[C], ss[C], p[C], q[C], la[C], ua[C], lb[C], ub[C], di[C], eai[C], ebi[C];
+    VD rho_a[C], rinv_a[C], rho_b[C], rinv_b[C];
+    VI cls[C];   // bits 0-1: acceleration row, bits 2-3: bound row
+    VD x[C], za[C], zb[C], ya[C], yb[C];
+    VD dx[C], dya[C], dyb[C];
+    VD nl[C], dinv[C], phi[kLevels], psi[kLevels];
+    double cs, cinv, nq_unscaled, nq_scaled;
+    RhoSet R;
+
+    AC_MEM explicit SpeedQP(const Ctx<C>& ctx) : c(ctx), n(ctx.n) {}
+
+    // speed_profile.py:26-59 / :131-150, then OSQP scale_data + set_rho_vec
+    AC_MEM void assemble_and_scale(const PathRegs<C>& path, double v_max_live, int localised)
+    {
+        const acmpc_config& g = *c.cfg;
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VI s = c.stage(j);
+            VB ok = vi_lt(s, n), row = vi_le(s, n - 2);
+            VD ak = vabs(path.kap[j]);
+            VD vdyn = vsqrt(VD(g.ay_max) / (ak + VD(1e-12)));
+            vdyn = vsel(ak < VD(g.ki_min), VD(v_max_live), vdyn);
+            VD v = vsel(vdyn < VD(v_max_live), vdyn, VD(v_max_live));
+            v = vsel(VD(g.v_min) > v, VD(g.v_min), v);
+            VD vb = v + VD(2.0);
+            if (g.has_end_velocity) vb = vsel(vi_eq(s, n - 1), VD(g.end_velocity), vb);
+            if (localised) vb = VD(v_max_live);
+            VD h = VD(1.0) / (VD(2.0) * path.dist[j]);
+            al[j] = vsel(row, -h, VD(0.0));
+            au[j] = vsel(row, h, VD(0.0));
+            ss[j] = vsel(ok, VD(1.0), VD(0.0));
+            p[j] = vsel(ok, VD(1.0), VD(0.0));
+            q[j] = vsel(ok, VD(-1.0) * vb, VD(0.0));
+            di[j] = VD(1.0), eai[j] = VD(1.0), ebi[j] = VD(1.0);
+            la[j] = vsel(row, VD(g.a_min), VD(0.0)), ua[j] = vsel(row, VD(g.a_max), VD(0.0));
+            lb[j] = vsel(ok, VD(g.v_min), VD(0.0)), ub[j] = vsel(ok, vb, VD(0.0));
+        }
+        cs = 1.0;
+        for (int pass = 0; pass < g.scaling; ++pass) {
+            // column / row inf-norms of [P A'; A 0]
+            VD aua[C], aup[C], d[C], dn[C];
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) aua[j] = vabs(au[j]);
+            pull_prev<C>(aua, aup);
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                VD m = vmax(vmax(vabs(p[j]), vabs(ss[j])), vmax(vabs(al[j]), aup[j]));
+                d[j] = inv_sqrt(limit_scaling(m));
+            }
+            pull_next<C>(d, dn);
+            VD psum = VD(0.0), qmax = VD(0.0);
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                VD ea = inv_sqrt(limit_scaling(vmax(vabs(al[j]), vabs(au[j]))));
+                al[j] = (al[j] * ea) * d[j];
+                au[j] = (au[j] * ea) * dn[j];
+                eai[j] = eai[j] * ea;
+                VD eb = inv_sqrt(limit_scaling(vabs(ss[j])));
+                ss[j] = (ss[j] * eb) * d[j];
+                ebi[j] = ebi[j] * eb;
+                p[j] = (p[j] * d[j]) * d[j];
+                q[j] = q[j] * d[j];
+                di[j] = di[j] * d[j];
+                psum = psum + vabs(p[j]);
+                qmax = vmax(qmax, vabs(q[j]));
+            }
+            double ct = fmax(wsum(psum) / (double)n, limit_scaling_u(wmax(qmax)));
+            ct = 1.0 / limit_scaling_u(ct);
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) p[j] = p[j] * VD(ct), q[j] = q[j] * VD(ct);
+            cs *= ct;
+        }
+        cinv = 1.0 / cs;
+        // scale bounds, classify rows, invert D/E, norm of q
+        VD nqu = VD(0.0), nqs = VD(0.0);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            la[j] = la[j] * eai[j], ua[j] = ua[j] * eai[j];
+            lb[j] = lb[j] * ebi[j], ub[j] = ub[j] * ebi[j];
+            cls[j] = row_class(la[j], ua[j]) | (row_class(lb[j], ub[j]) << 2);
+            di[j] = VD(1.0) / di[j];
+            eai[j] = VD(1.0) / eai[j];
+            ebi[j] = VD(1.0) / ebi[j];
+            nqu = vmax(nqu, vabs(di[j] * q[j]));
+            nqs = vmax(nqs, vabs(q[j]));
+        }
+        nq_unscaled = wmax(nqu);
+        nq_scaled = wmax(nqs);
+    }
+
+    // reduced matrix K = P + sigma + A' rho A (tridiagonal) -> LDL' -> scan coefficients.
+    // scratch: two per-stage columns of shared memory (K_N+0, K_N+1: dead until the control QP)
+    AC_MEM void factor()
+    {
+        const double sigma = c.cfg->sigma;
+        VD t[C], tp[C];
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            rho_a[j] = R.of(cls[j], 0), rinv_a[j] = R.inv_of(cls[j], 0);
+            rho_b[j] = R.of(cls[j], 2), rinv_b[j] = R.inv_of(cls[j], 2);
+            t[j] = rho_a[j] * au[j] * au[j];
+        }
+        pull_prev<C>(t, tp);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VD d = p[j] + VD(sigma) + rho_b[j] * ss[j] * ss[j] + rho_a[j] * al[j] * al[j] + tp[j];
+            c.st(K_N + 0, j, d);
+            c.st(K_N + 1, j, rho_a[j] * al[j] * au[j]);   // (i, i+1) entry, 0 without a row
+        }
+        warp_sync();
+        // serial LDL' (every lane runs it on broadcast reads; lane 0 publishes)
+        {
+            double oprev = 0.0, dprev = 0.0;
+            int s = 0;
+            for (int l = 0; l < 32 && s < n; ++l)
+                for (int j = 0; j < C && s < n; ++j, ++s) {
+                    double* pd = c.col(K_N + 0, j) + l;
+                    double* po = c.col(K_N + 1, j) + l;
+                    double dd = *pd, oo = *po;
+                    double lw = oprev * dprev;          // L_{s,s-1}
+                    double piv = dd - lw * oprev;
+                    dprev = 1.0 / piv;
+                    oprev = oo;
+                    AC_LANE0
+                    {
+                        *pd = dprev;
+                        *po = -lw;
+                    }
+                }
+        }
+        warp_sync();
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VB ok = vi_lt(c.stage(j), n);
+            dinv[j] = vsel(ok, c.ld(K_N + 0, j), VD(0.0));
+            nl[j] = vsel(ok, c.ld(K_N + 1, j), VD(0.0));
+        }
+        warp_sync();
+        VD f = nl[0];
+        AC_UNROLL
+        for (int j = 1; j < C; ++j) f = nl[j] * f;
+        AC_UNROLL
+        for (int L = 0; L < kLevels; ++L) {
+            phi[L] = f;
+            psi[L] = shfl_down0(f, 1 << L);
+            f = f * shfl_up0(f, 1 << L);
+        }
+    }
+
+    // x~ = K^{-1} r
+    AC_MEM void kkt_solve(const VD (&r)[C], VD (&xt)[C])
+    {
+        VD y[C], w[C];
+        VD Y = r[0];
+        AC_UNROLL
+        for (int j = 1; j < C; ++j) Y = r[j] + nl[j] * Y;
+        AC_UNROLL
+        for (int L = 0; L < kLevels; ++L) Y = Y + phi[L] * shfl_up_raw(Y, 1 << L);   // phi = 0 on lanes < 2^L
+        VD yin = shfl_up_raw(Y, 1);                                                  // nl[0] = 0 on lane 0
+        y[0] = r[0] + nl[0] * yin;
+        AC_UNROLL
+        for (int j = 1; j + 1 < C; ++j) y[j] = r[j] + nl[j] * y[j - 1];
+        if (C > 1) y[C - 1] = Y;
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) w[j] = y[j] * dinv[j];
+        VD a = VD(0.0);
+        if (C > 1) {
+            a = w[C - 2];
+            AC_UNROLL
+            for (int j = C - 3; j >= 0; --j) a = w[j] + nl[j + 1] * a;
+        }
+        VD Z = w[C - 1] + shfl_down0(nl[0] * a, 1);
+        AC_UNROLL
+        for (int L = 0; L < kLevels; ++L) Z = Z + psi[L] * shfl_down_raw(Z, 1 << L);   // psi = 0 beyond lane 31
+        xt[C - 1] = Z;
+        AC_UNROLL
+        for (int j = C - 2; j >= 0; --j) xt[j] = w[j] + nl[j + 1] * xt[j + 1];
+    }
+
+    AC_MEM void compute_norms(Norms& N)
+    {
+        VD v[12];
+        for (int t = 0; t < 12; ++t) v[t] = VD(0.0);
+        VD xn[C], t[C], tp[C];
+        pull_next<C>(x, xn);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) t[j] = au[j] * ya[j];
+        pull_prev<C>(t, tp);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VD aty = ss[j] * yb[j] + al[j] * ya[j] + tp[j];
+            acc_row(v, al[j] * x[j] + au[j] * xn[j], za[j], eai[j]);
+            acc_row(v, ss[j] * x[j], zb[j], ebi[j]);
+            acc_col(v, q[j], p[j] * x[j], aty, di[j]);
+        }
+        finish_norms(v, cinv, nq_unscaled, nq_scaled, N);
+    }
+
+    AC_MEM int primal_infeasible(double eps)
+    {
+        VD nrm = VD(0.0), lhs = VD(0.0);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            dya[j] = project_dy(dya[j], la[j], ua[j]);
+            dyb[j] = project_dy(dyb[j], lb[j], ub[j]);
+            nrm = vmax(nrm, vmax(vabs(dya[j] / eai[j]), vabs(dyb[j] / ebi[j])));
+            lhs = lhs + support(dya[j], la[j], ua[j]) + support(dyb[j], lb[j], ub[j]);
+        }
+        double nr = wmax(nrm), lh = wsum(lhs);
+        if (uni(!(nr > eps) || !(lh < -eps * nr))) return 0;
+        VD t[C], tp[C], m = VD(0.0);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) t[j] = au[j] * dya[j];
+        pull_prev<C>(t, tp);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) m = vmax(m, vabs(di[j] * (ss[j] * dyb[j] + al[j] * dya[j] + tp[j])));
+        return wmax(m) < eps * nr;
+    }
+
+    AC_MEM int dual_infeasible(double eps)
+    {
+        VD nrm = VD(0.0), qdx = VD(0.0), pm = VD(0.0);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            nrm = vmax(nrm, vabs(dx[j] / di[j]));
+            qdx = qdx + q[j] * dx[j];
+            pm = vmax(pm, vabs(di[j] * (p[j] * dx[j])));
+        }
+        double nr = wmax(nrm), qd = wsum(qdx), pmx = wmax(pm);
+        if (uni(!(nr > eps) || !(qd < -cs * eps * nr) || !(pmx < cs * eps * nr))) return 0;
+        VD dn[C];
+        pull_next<C>(dx, dn);
+        VB bad = vb_all(false);
+        const VD lim = VD(eps * nr);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VD a = eai[j] * (al[j] * dx[j] + au[j] * dn[j]);
+            bad = bad | ((ua[j] < VD(kBig)) & (a > lim)) | ((la[j] > VD(-kBig)) & (a < -lim));
+            VD b = ebi[j] * (ss[j] * dx[j]);
+            bad = bad | ((ub[j] < VD(kBig)) & (b > lim)) | ((lb[j] > VD(-kBig)) & (b < -lim));
+        }
+        return !wany(bad);
+    }
+
+    // check_termination(work, approximate): returns status or 0 (continue)
+    AC_MEM int check(const Norms& N, int approximate)
+    {
+        const acmpc_config& g = *c.cfg;
+        double k = approximate ? 10.0 : 1.0;
+        if (uni(N.pri > kInfty || N.dua > kInfty)) return ACMPC_NON_CVX;
+        double eps_p = k * g.eps_abs + k * g.eps_rel * fmax(N.nz, N.nAx);
+        double eps_d = k * g.eps_abs + k * g.eps_rel * cinv * fmax(N.nq, fmax(N.nAty, N.nPx));
+        int p_ok = uni(N.pri < eps_p), d_ok = uni(N.dua < eps_d);
+        int p_inf = 0, d_inf = 0;
+        if (!p_ok) p_inf = primal_infeasible(k * g.eps_prim_inf);
+        if (!d_ok) d_inf = dual_infeasible(k * g.eps_dual_inf);
+        if (p_ok && d_ok) return approximate ? ACMPC_SOLVED_INACCURATE : ACMPC_SOLVED;
+        if (p_inf) return approximate ? ACMPC_PRIMAL_INFEASIBLE_INACCURATE : ACMPC_PRIMAL_INFEASIBLE;
+        if (d_inf) return approximate ? ACMPC_DUAL_INFEASIBLE_INACCURATE : ACMPC_DUAL_INFEASIBLE;
+        return 0;
+    }
+
+    // osqp_solve, cold start.  Result (unscaled v) -> vout.
+    AC_MEM void solve(SolveInfo& info, VD (&vout)[C])
+    {
+        const acmpc_config& g = *c.cfg;
+        const double alpha = g.alpha, sigma = g.sigma;
+        R.set(clampu(g.rho, kRhoMin, kRhoMax));
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            x[j] = za[j] = zb[j] = ya[j] = yb[j] = VD(0.0);
+            dx[j] = dya[j] = dyb[j] = VD(0.0);
+        }
+        factor();
+        Norms N;
+        int status = 0, iter = 0, updates = 0;
+        for (;;) {
+            ++iter;
+            VD r[C], xt[C], xn[C], t[C], tp[C];
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                VD wa = rho_a[j] * za[j] - ya[j];
+                t[j] = au[j] * wa;
+                r[j] = VD(sigma) * x[j] - q[j] + ss[j] * (rho_b[j] * zb[j] - yb[j]) + al[j] * wa;
+            }
+            pull_prev<C>(t, tp);
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) r[j] = r[j] + tp[j];
+            kkt_solve(r, xt);
+            pull_next<C>(xt, xn);
+            const bool checked = (g.check_termination > 0 && iter % g.check_termination == 0);
+            const bool last = iter >= g.max_iter;
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                {
+                    VD zt = al[j] * xt[j] + au[j] * xn[j];
+                    VD zh = VD(alpha) * zt + VD(1.0 - alpha) * za[j];
+                    VD zn = vclamp(zh + rinv_a[j] * ya[j], la[j], ua[j]);
+                    VD dy = rho_a[j] * (zh - zn);
+                    za[j] = zn;
+                    ya[j] = ya[j] + dy;
+                    dya[j] = dy;
+                }
+                {
+                    VD zt = ss[j] * xt[j];
+                    VD zh = VD(alpha) * zt + VD(1.0 - alpha) * zb[j];
+                    VD zn = vclamp(zh + rinv_b[j] * yb[j], lb[j], ub[j]);
+                    VD dy = rho_b[j] * (zh - zn);
+                    zb[j] = zn;
+                    yb[j] = yb[j] + dy;
+                    dyb[j] = dy;
+                }
+                VD xnew = VD(alpha) * xt[j] + VD(1.0 - alpha) * x[j];
+                dx[j] = xnew - x[j];
+                x[j] = xnew;
+            }
+            const bool adapt = g.adaptive_rho && g.adaptive_rho_interval > 0 && iter % g.adaptive_rho_interval == 0;
+            if (checked || adapt || last) compute_norms(N);
+            // osqp_solve's order: exact check (every check_termination iterations) -> adaptive rho ->
+            // at the iteration limit the exact check if it has not just run, then the 10x "inaccurate" one.
+            // Written as a two-phase loop so that check()/factor() are inlined once.
+            AC_NOUNROLL
+            for (int phase = 0; phase < 2 && !uni(status != 0); ++phase) {
+                if (phase == 0 ? checked : last) {
+                    const int lo = (phase == 1 && checked) ? 1 : 0;
+                    AC_NOUNROLL
+                    for (int approx = lo; approx <= phase && !uni(status != 0); ++approx) status = check(N, approx);
+                    if (phase == 1 && !status) status = ACMPC_MAX_ITER_REACHED;
+                }
+                if (phase == 0 && !uni(status != 0) && adapt) {
+                    double rn = rho_estimate(N, R.rho);
+                    if (uni(rn > R.rho * g.adaptive_rho_tolerance || rn < R.rho / g.adaptive_rho_tolerance)) {
+                        R.set(rn);
+                        ++updates;
+                        factor();
+                    }
+                }
+            }
+            if (uni(status != 0)) break;
+        }
+        info.status = status, info.iter = iter, info.rho_updates = updates;
+        info.pri_res = N.pri, info.dua_res = N.dua;
+        VD obj = VD(0.0);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            obj = obj + (VD(0.5) * p[j] * x[j] * x[j] + q[j] * x[j]);
+            vout[j] = x[j] / di[j];
+        }
+        info.obj_val = final_obj(status, wsum(obj) * cinv);
+    }
+};
+
+// ================================================================================================
+// Control QP (solvers/control.py + dynamics.py:65-103).  Stage s owns x_s = (e_y, e_psi, t) as local
+// variables 0..2 and u_{s-1} = (v, kappa_cmd) as local variables 3,4 (stage 0 has no input: its slots
+// are all-zero dummies, as are the slots of stages >= H).
+// ================================================================================================
+template <int C>
+struct ControlQP {
+    const Ctx<C>& c;
+    int n, H;
+    VD x[C][5], zb[C][5], yb[C][5], ye[C][3], ze[C][3];
+    VD dx[C][5], dyb[C][5], dye[C][3];
+    VI cls[C];   // class of bound row j in bits 2j, 2j+1
+    double cs, cinv, nq_unscaled, nq_scaled;
+    RhoSet R;
+
+    AC_MEM explicit ControlQP(const Ctx<C>& ctx) : c(ctx), n(ctx.n), H(ctx.H) {}
+
+    // linearise + stack (dynamics.py:65-103, solvers/control.py:26-79), OSQP scale_data (Ruiz) and
+    // set_rho_vec classes; the scaled problem goes to shared memory.
+    AC_MEM void setup(const PathRegs<C>& path, const VD (&vel)[C], double offset)
+    {
+        const acmpc_config& g = *c.cfg;
+        const double eps = 1e-12;
+        // t2s of the state (offset, 0, pi/2) on waypoint 0 (spatial_mpc.py:186-189, dynamics.py:23-40)
+        const double psi0 = lane_value(path.psi[0], 0), xs0 = lane_value(path.xs[0], 0),
+                     ys0 = lane_value(path.ys[0], 0);
+        double x0[3];
+        x0[0] = cos(psi0) * (0.0 - ys0) - sin(psi0) * (offset - xs0);
+        x0[1] = np_mod_u((kPi / 2.0 - psi0) + kPi, 2.0 * kPi) - kPi;
+        x0[2] = 0.0;
+        const double margin = g.width / 2.0;
+        const double kmax = tan(g.delta_max) / g.wheelbase;
+
+        VD m[C][3], a[C][6], b[C][2], s[C][5], P[C][5], q[C][2], D[C][5], EE[C][3], EB[C][5];
+        VD dp[C], kp[C], vp[C], wp[C];
+        pull_prev<C>(path.dist, dp);
+        pull_prev<C>(path.kap, kp);
+        pull_prev<C>(vel, vp);
+        pull_prev<C>(path.wid, wp);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VI st = c.stage(j);
+            VB isx = vi_lt(st, H), hasA = vi_lt(st, n), hasU = vi_ge(st, 1) & isx;
+            const VD d = path.dist[j], ka = path.kap[j], v = vel[j];
+            const VD one_x = vsel(isx, VD(1.0), VD(0.0)), one_a = vsel(hasA, VD(1.0), VD(0.0)),
+                     one_u = vsel(hasU, VD(1.0), VD(0.0));
+            for (int r = 0; r < 3; ++r) m[j][r] = -one_x;
+            a[j][0] = one_a;
+            a[j][1] = vsel(hasA, d, VD(0.0));
+            a[j][2] = vsel(hasA, -(ka * ka) * d, VD(0.0));
+            a[j][3] = one_a;
+            a[j][4] = vsel(hasA, -ka / (v * d + VD(eps)), VD(0.0));
+            a[j][5] = one_a;
+            b[j][0] = vsel(hasU, dp[j], VD(0.0));
+            b[j][1] = vsel(hasU, VD(-1.0) / (vp[j] * vp[j] * dp[j] + VD(eps)), VD(0.0));
+            for (int e = 0; e < 3; ++e) s[j][e] = one_x;
+            s[j][3] = one_u, s[j][4] = one_u;
+            for (int e = 0; e < 3; ++e) P[j][e] = vsel(hasA, VD(g.step_cost[e]), vsel(isx, VD(g.final_cost[e]), VD(0.0)));
+            P[j][3] = vsel(hasU, VD(g.r_term[0]), VD(0.0));
+            P[j][4] = vsel(hasU, VD(g.r_term[1]), VD(0.0));
+            q[j][0] = vsel(hasU, VD(-g.r_term[0]) * vp[j], VD(0.0));
+            q[j][1] = vsel(hasU, VD(-g.r_term[1]) * kp[j], VD(0.0));
+            for (int e = 0; e < 5; ++e) D[j][e] = VD(1.0), EB[j][e] = VD(1.0);
+            for (int r = 0; r < 3; ++r) EE[j][r] = VD(1.0);
+        }
+        // ---- Ruiz equilibration
+        cs = 1.0;
+        const int nv_total = 5 * H - 2;
+        for (int pass = 0; pass < g.scaling; ++pass) {
+            VD pr[C][3], prp[C][3], ee[C][3], een[C][3], dd[C][5];
+            // partial row norms of block s+1 from the columns of stage s
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                pr[j][0] = vmax(vabs(a[j][0]), vabs(a[j][1]));
+                pr[j][1] = vmax(vabs(a[j][2]), vabs(a[j][3]));
+                pr[j][2] = vmax(vabs(a[j][4]), vabs(a[j][5]));
+            }
+            pull_prev_k<C, 3>(pr, prp);
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                VD am[3], sm[5], pm[5];
+                for (int r = 0; r < 3; ++r) am[r] = vabs(m[j][r]);
+                for (int e = 0; e < 5; ++e) sm[e] = vabs(s[j][e]), pm[e] = vabs(P[j][e]);
+                VD a11 = vabs(a[j][0]), a12 = vabs(a[j][1]), a21 = vabs(a[j][2]), a22 = vabs(a[j][3]),
+                   a31 = vabs(a[j][4]), a33 = vabs(a[j][5]), b22 = vabs(b[j][0]), b31 = vabs(b[j][1]);
+                VD cn[5];
+                cn[0] = vmax(vmax(vmax(am[0], a11), vmax(a21, a31)), vmax(sm[0], pm[0]));
+                cn[1] = vmax(vmax(am[1], a12), vmax(a22, vmax(sm[1], pm[1])));
+                cn[2] = vmax(vmax(am[2], a33), vmax(sm[2], pm[2]));
+                cn[3] = vmax(b31, vmax(sm[3], pm[3]));
+                cn[4] = vmax(b22, vmax(sm[4], pm[4]));
+                for (int e = 0; e < 5; ++e) dd[j][e] = inv_sqrt(limit_scaling(cn[e]));
+                ee[j][0] = inv_sqrt(limit_scaling(vmax(am[0], prp[j][0])));
+                ee[j][1] = inv_sqrt(limit_scaling(vmax(vmax(am[1], b22), prp[j][1])));
+                ee[j][2] = inv_sqrt(limit_scaling(vmax(vmax(am[2], b31), prp[j][2])));
+            }
+            pull_next_k<C, 3>(ee, een);
+            VD psum = VD(0.0), qmax = VD(0.0);
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                for (int r = 0; r < 3; ++r) {
+                    m[j][r] = (m[j][r] * ee[j][r]) * dd[j][r];
+                    EE[j][r] = EE[j][r] * ee[j][r];
+                }
+                a[j][0] = (a[j][0] * een[j][0]) * dd[j][0];
+                a[j][1] = (a[j][1] * een[j][0]) * dd[j][1];
+                a[j][2] = (a[j][2] * een[j][1]) * dd[j][0];
+                a[j][3] = (a[j][3] * een[j][1]) * dd[j][1];
+                a[j][4] = (a[j][4] * een[j][2]) * dd[j][0];
+                a[j][5] = (a[j][5] * een[j][2]) * dd[j][2];
+                b[j][0] = (b[j][0] * ee[j][1]) * dd[j][4];
+                b[j][1] = (b[j][1] * ee[j][2]) * dd[j][3];
+                for (int e = 0; e < 5; ++e) {
+                    VD eb = inv_sqrt(limit_scaling(vabs(s[j][e])));
+                    s[j][e] = (s[j][e] * eb) * dd[j][e];
+                    EB[j][e] = EB[j][e] * eb;
+                    D[j][e] = D[j][e] * dd[j][e];
+                    P[j][e] = (P[j][e] * dd[j][e]) * dd[j][e];
+                    psum = psum + vabs(P[j][e]);
+                }
+                for (int e = 0; e < 2; ++e) {
+                    q[j][e] = q[j][e] * dd[j][3 + e];
+                    qmax = vmax(qmax, vabs(q[j][e]));
+                }
+            }
+            double ct = fmax(wsum(psum) / (double)nv_total, limit_scaling_u(wmax(qmax)));
+            ct = 1.0 / limit_scaling_u(ct);
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                for (int e = 0; e < 5; ++e) P[j][e] = P[j][e] * VD(ct);
+                for (int e = 0; e < 2; ++e) q[j][e] = q[j][e] * VD(ct);
+            }
+            cs *= ct;
+        }
+        cinv = 1.0 / cs;
+        // ---- bounds (solvers/control.py:47-70,121-149, clipped to +-OSQP_INFTY), classes, stores
+        VD nqu = VD(0.0), nqs = VD(0.0);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VI st = c.stage(j);
+            VB isx = vi_lt(st, H), hasU = vi_ge(st, 1) & isx, first = vi_eq(st, 0);
+            VD lo[5], hi[5], be[3];
+            lo[0] = vsel(first, VD(x0[0]), (-wp[j] / VD(2.0)) + VD(margin));
+            hi[0] = vsel(first, VD(x0[0]), (wp[j] / VD(2.0)) - VD(margin));
+            lo[1] = VD(-kInfty), hi[1] = VD(kInfty);
+            lo[2] = VD(0.01), hi[2] = VD(kInfty);
+            lo[3] = VD(g.input_v_min - 0.1), hi[3] = VD(g.input_v_max + 0.1);
+            lo[4] = VD(-kmax), hi[4] = VD(kmax);
+            const VD b31raw = VD(-1.0) / (vp[j] * vp[j] * dp[j] + VD(eps)), f3 = VD(1.0) / (vp[j] * dp[j] + VD(eps));
+            be[0] = vsel(first, VD(-x0[0]), VD(0.0) * vp[j] + VD(0.0) * kp[j] - VD(0.0));
+            be[1] = vsel(first, VD(-x0[1]), VD(0.0) * vp[j] + dp[j] * kp[j] - VD(0.0));
+            be[2] = vsel(first, VD(-x0[2]), b31raw * vp[j] + VD(0.0) * kp[j] - f3);
+            VI bits = vi_all(0);
+            for (int e = 0; e < 5; ++e) {
+                VB real = (e < 3) ? isx : hasU;
+                VD l = vsel(real, lo[e] * EB[j][e], VD(0.0)), u = vsel(real, hi[e] * EB[j][e], VD(0.0));
+                bits = bits | (row_class(l, u) << (2 * e));
+                c.st(K_LB + e, j, l), c.st(K_UB + e, j, u);
+                c.st(K_S + e, j, s[j][e]), c.st(K_P + e, j, P[j][e]);
+                VD dinv = VD(1.0) / D[j][e];
+                c.st(K_DI + e, j, dinv), c.st(K_EBI + e, j, VD(1.0) / EB[j][e]);
+                if (e >= 3) {
+                    nqu = vmax(nqu, vabs(dinv * q[j][e - 3]));
+                    nqs = vmax(nqs, vabs(q[j][e - 3]));
+                }
+            }
+            cls[j] = bits;
+            for (int r = 0; r < 3; ++r) {
+                c.st(K_BE + r, j, vsel(isx, be[r] * EE[j][r], VD(0.0)));
+                c.st(K_EEI + r, j, VD(1.0) / EE[j][r]);
+                c.st(K_M + r, j, m[j][r]);
+            }
+            for (int e = 0; e < 6; ++e) c.st(K_A + e, j, a[j][e]);
+            c.st(K_B + 0, j, b[j][0]), c.st(K_B + 1, j, b[j][1]);
+            c.st(K_Q + 0, j, q[j][0]), c.st(K_Q + 1, j, q[j][1]);
+        }
+        nq_unscaled = wmax(nqu);
+        nq_scaled = wmax(nqs);
+        warp_sync();
+    }
+
+    // Reduced matrix, analytic elimination of the inputs, block LDL' over the states, scan matrices.
+    AC_MEM void factor()
+    {
+        const double sigma = c.cfg->sigma, re = R.rho_eq;
+        VD g2[C][2], g2n[C][2], av[C][6], ap[C][6];
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            for (int e = 0; e < 5; ++e) c.st(K_RHO + e, j, R.of(cls[j], 2 * e)), c.st(K_RINV + e, j, R.inv_of(cls[j], 2 * e));
+            VD b22 = c.ld(K_B + 0, j), b31 = c.ld(K_B + 1, j), s3 = c.ld(K_S + 3, j), s4 = c.ld(K_S + 4, j);
+            VD kv = c.ld(K_P + 3, j) + VD(sigma) + R.of(cls[j], 6) * s3 * s3 + VD(re) * b31 * b31;
+            VD kk = c.ld(K_P + 4, j) + VD(sigma) + R.of(cls[j], 8) * s4 * s4 + VD(re) * b22 * b22;
+            VD iv = VD(1.0) / kv, ik = VD(1.0) / kk;
+            VD rb31 = VD(re) * b31, rb22 = VD(re) * b22;
+            c.st(K_IV, j, iv), c.st(K_IK, j, ik), c.st(K_RB31, j, rb31), c.st(K_RB22, j, rb22);
+            g2[j][0] = iv * rb31 * rb31;   // gv
+            g2[j][1] = ik * rb22 * rb22;   // gk
+            for (int e = 0; e < 6; ++e) av[j][e] = c.ld(K_A + e, j);
+        }
+        pull_next_k<C, 2>(g2, g2n);
+        pull_prev_k<C, 6>(av, ap);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VD m0 = c.ld(K_M + 0, j), m1 = c.ld(K_M + 1, j), m2 = c.ld(K_M + 2, j);
+            VD s0 = c.ld(K_S + 0, j), s1 = c.ld(K_S + 1, j), s2 = c.ld(K_S + 2, j);
+            const VD gv = g2[j][0], gk = g2[j][1], gvn = g2n[j][0], gkn = g2n[j][1];
+            const VD a11 = av[j][0], a12 = av[j][1], a21 = av[j][2], a22 = av[j][3], a31 = av[j][4], a33 = av[j][5];
+            VD k00 = c.ld(K_P + 0, j) + VD(sigma) + R.of(cls[j], 0) * s0 * s0 + VD(re) * m0 * m0;
+            VD k11 = c.ld(K_P + 1, j) + VD(sigma) + R.of(cls[j], 2) * s1 * s1 + VD(re) * m1 * m1;
+            VD k22 = c.ld(K_P + 2, j) + VD(sigma) + R.of(cls[j], 4) * s2 * s2 + VD(re) * m2 * m2;
+            // elimination of the own input u_{s-1}
+            k11 = k11 - gk * m1 * m1;
+            k22 = k22 - gv * m2 * m2;
+            // A_s' rho_eq A_s and the elimination of u_s (owned by stage s+1)
+            k00 = k00 + VD(re) * (a11 * a11 + a21 * a21 + a31 * a31) - (gvn * a31 * a31 + gkn * a21 * a21);
+            VD k10 = VD(re) * (a11 * a12 + a21 * a22) - gkn * a21 * a22;
+            k11 = k11 + VD(re) * (a12 * a12 + a22 * a22) - gkn * a22 * a22;
+            VD k20 = VD(re) * (a31 * a33) - gvn * a31 * a33;
+            k22 = k22 + VD(re) * (a33 * a33) - gvn * a33 * a33;
+            c.st(K_SI + 0, j, k00), c.st(K_SI + 1, j, k10), c.st(K_SI + 2, j, k11);
+            c.st(K_SI + 3, j, k20), c.st(K_SI + 4, j, VD(0.0)), c.st(K_SI + 5, j, k22);
+            // S_{s,s-1}: rows of x_s, columns of x_{s-1} (entries of A_{s-1})
+            const VD p11 = ap[j][0], p12 = ap[j][1], p21 = ap[j][2], p22 = ap[j][3], p31 = ap[j][4], p33 = ap[j][5];
+            c.st(K_N + 0, j, m0 * VD(re) * p11);
+            c.st(K_N + 1, j, m0 * VD(re) * p12);
+            c.st(K_N + 2, j, VD(0.0));
+            c.st(K_N + 3, j, m1 * (VD(re) * p21 - gk * p21));
+            c.st(K_N + 4, j, m1 * (VD(re) * p22 - gk * p22));
+            c.st(K_N + 5, j, VD(0.0));
+            c.st(K_N + 6, j, m2 * (VD(re) * p31 - gv * p31));
+            c.st(K_N + 7, j, VD(0.0));
+            c.st(K_N + 8, j, m2 * (VD(re) * p33 - gv * p33));
+        }
+        warp_sync();
+        // serial block LDL': Sigma_s = S_ss - G_s S_{s,s-1}', G_s = S_{s,s-1} Sigma_{s-1}^{-1}; N_s = -G_s.
+        // Every lane runs the recurrence on broadcast reads; lane 0 publishes N_s and Sigma_s^{-1} in place.
+        {
+            double i00 = 0, i10 = 0, i11 = 0, i20 = 0, i21 = 0, i22 = 0;
+            int s = 0;
+            for (int l = 0; l < 32 && s < H; ++l)
+                for (int j = 0; j < C && s < H; ++j, ++s) {
+                    double* SI = c.col(K_SI, j) + l;
+                    double* NN = c.col(K_N, j) + l;
+                    const int st = C * 32;   // distance between consecutive fields
+                    double a00 = SI[0 * st], a10 = SI[1 * st], a11 = SI[2 * st];
+                    double a20 = SI[3 * st], a21 = SI[4 * st], a22 = SI[5 * st];
+                    double gg[9];
+                    {
+                        // structural zeros of S_{s,s-1}: (0,2) (1,2) (2,1)
+                        const double o00 = NN[0 * st], o01 = NN[1 * st], o10 = NN[3 * st], o11 = NN[4 * st];
+                        const double o20 = NN[6 * st], o22 = NN[8 * st];
+                        gg[0] = o00 * i00 + o01 * i10, gg[1] = o00 * i10 + o01 * i11, gg[2] = o00 * i20 + o01 * i21;
+                        gg[3] = o10 * i00 + o11 * i10, gg[4] = o10 * i10 + o11 * i11, gg[5] = o10 * i20 + o11 * i21;
+                        gg[6] = o20 * i00 + o22 * i20, gg[7] = o20 * i10 + o22 * i21, gg[8] = o20 * i20 + o22 * i22;
+                        a00 -= gg[0] * o00 + gg[1] * o01;
+                        a10 -= gg[3] * o00 + gg[4] * o01;
+                        a11 -= gg[3] * o10 + gg[4] * o11;
+                        a20 -= gg[6] * o00 + gg[7] * o01;
+                        a21 -= gg[6] * o10 + gg[7] * o11;
+                        a22 -= gg[6] * o20 + gg[8] * o22;
+                    }
+                    // inverse of the SPD 3x3 through LDL'
+                    double d0i = 1.0 / a00;
+                    double l10 = a10 * d0i, l20 = a20 * d0i;
+                    double d1i = 1.0 / (a11 - l10 * a10);
+                    double l21 = (a21 - l20 * a10) * d1i;
+                    double d2i = 1.0 / (a22 - l20 * a20 - l21 * (a21 - l20 * a10));
+                    double w20 = l10 * l21 - l20;   // (L^{-1})_{20}
+                    i22 = d2i;
+                    i21 = -l21 * d2i;
+                    i20 = w20 * d2i;
+                    i11 = d1i + l21 * l21 * d2i;
+                    i10 = -l10 * d1i - l21 * w20 * d2i;
+                    i00 = d0i + l10 * l10 * d1i + w20 * w20 * d2i;
+                    AC_LANE0
+                    {
+                        SI[0 * st] = i00, SI[1 * st] = i10, SI[2 * st] = i11;
+                        SI[3 * st] = i20, SI[4 * st] = i21, SI[5 * st] = i22;
+                        for (int e = 0; e < 9; ++e) NN[e * st] = -gg[e];
+                    }
+                }
+        }
+        warp_sync();
+        // lane-level prefix products for the scans: level L maps the carry of lane l - 2^L to lane l
+        VD F[9];
+        for (int e = 0; e < 9; ++e) F[e] = c.ld(K_N + e, 0);
+        AC_UNROLL
+        for (int j = 1; j < C; ++j) {
+            VD Nj[9], T[9];
+            for (int e = 0; e < 9; ++e) Nj[e] = c.ld(K_N + e, j);
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 3; ++q)
+                    T[3 * r + q] = Nj[3 * r] * F[q] + Nj[3 * r + 1] * F[3 + q] + Nj[3 * r + 2] * F[6 + q];
+            for (int e = 0; e < 9; ++e) F[e] = T[e];
+        }
+        for (int L = 0; L < kLevels; ++L) {
+            VD U[9], T[9];
+            for (int e = 0; e < 9; ++e) {
+                st_lane(c.scan(L, e), F[e]);
+                U[e] = shfl_up0(F[e], 1 << L);
+            }
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 3; ++q)
+                    T[3 * r + q] = F[3 * r] * U[q] + F[3 * r + 1] * U[3 + q] + F[3 * r + 2] * U[6 + q];
+            for (int e = 0; e < 9; ++e) F[e] = T[e];
+        }
+        warp_sync();
+    }
+
+    // x~ = Schur^{-1} r for the state part: two affine scans over the stages (see file header)
+    AC_MEM void block_solve(const VD (&r)[C][3], VD (&xt)[C][3])
+    {
+        VD y[C][3], w[C][3], M[9];
+        // forward: local pass with zero carry-in, scan over lanes, local fix-up
+        VD Y[3] = {r[0][0], r[0][1], r[0][2]};
+        AC_UNROLL
+        for (int j = 1; j < C; ++j) {
+            for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, j);
+            VD T[3] = {r[j][0], r[j][1], r[j][2]};
+            mv_acc(M, Y, T);
+            Y[0] = T[0], Y[1] = T[1], Y[2] = T[2];
+        }
+        // (the level matrices are zero on lanes < 2^L and N_0 is zero on lane 0: raw shuffles suffice)
+        {
+            const double* sp = c.scan(0, 0);
+            AC_NOUNROLL
+            for (int L = 0; L < kLevels; ++L, sp += 9 * 32) {
+                VD U[3];
+                for (int e = 0; e < 3; ++e) U[e] = shfl_up_raw(Y[e], 1 << L);
+                for (int e = 0; e < 9; ++e) M[e] = ld_lane(sp + e * 32);
+                mv_acc(M, U, Y);
+            }
+        }
+        {
+            VD U[3];
+            for (int e = 0; e < 3; ++e) U[e] = shfl_up_raw(Y[e], 1);
+            for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, 0);
+            for (int e = 0; e < 3; ++e) y[0][e] = r[0][e];
+            mv_acc(M, U, y[0]);
+        }
+        AC_UNROLL
+        for (int j = 1; j + 1 < C; ++j) {
+            for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, j);
+            for (int e = 0; e < 3; ++e) y[j][e] = r[j][e];
+            mv_acc(M, y[j - 1], y[j]);
+        }
+        if (C > 1)
+            for (int e = 0; e < 3; ++e) y[C - 1][e] = Y[e];
+        // diagonal
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VD i00 = c.ld(K_SI + 0, j), i10 = c.ld(K_SI + 1, j), i11 = c.ld(K_SI + 2, j);
+            VD i20 = c.ld(K_SI + 3, j), i21 = c.ld(K_SI + 4, j), i22 = c.ld(K_SI + 5, j);
+            w[j][0] = i00 * y[j][0] + i10 * y[j][1] + i20 * y[j][2];
+            w[j][1] = i10 * y[j][0] + i11 * y[j][1] + i21 * y[j][2];
+            w[j][2] = i20 * y[j][0] + i21 * y[j][1] + i22 * y[j][2];
+        }
+        // backward: x_s = w_s + N_{s+1}' x_{s+1}; carry = x of the lane's LAST stage
+        VD A[3] = {VD(0.0), VD(0.0), VD(0.0)};
+        if (C > 1) {
+            for (int e = 0; e < 3; ++e) A[e] = w[C - 2][e];
+            AC_UNROLL
+            for (int j = C - 3; j >= 0; --j) {
+                for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, j + 1);
+                VD T[3] = {w[j][0], w[j][1], w[j][2]};
+                mtv_acc(M, A, T);
+                A[0] = T[0], A[1] = T[1], A[2] = T[2];
+            }
+        }
+        VD Z[3];
+        {
+            VD Hh[3] = {VD(0.0), VD(0.0), VD(0.0)};
+            if (C > 1) {
+                for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, 0);
+                mtv_acc(M, A, Hh);
+            }
+            for (int e = 0; e < 3; ++e) Z[e] = w[C - 1][e] + shfl_down0(Hh[e], 1);
+        }
+        {
+            const double* sp = c.scan(0, 0);
+            AC_NOUNROLL
+            for (int L = 0; L < kLevels; ++L, sp += 9 * 32) {
+                VD U[3];
+                for (int e = 0; e < 3; ++e) U[e] = shfl_down0(Z[e], 1 << L);
+                for (int e = 0; e < 9; ++e) M[e] = ld_lane_at(sp + e * 32, 1 << L);
+                mtv_acc(M, U, Z);
+            }
+        }
+        for (int e = 0; e < 3; ++e) xt[C - 1][e] = Z[e];
+        AC_UNROLL
+        for (int j = C - 2; j >= 0; --j) {
+            for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, j + 1);
+            for (int e = 0; e < 3; ++e) xt[j][e] = w[j][e];
+            mtv_acc(M, xt[j + 1], xt[j]);
+        }
+    }
+
+    // One ADMM iteration (osqp_solve loop body): rhs, reduced solve, recover inputs, relax, project, duals.
+    AC_MEM void iterate(bool keep_delta)
+    {
+        const double sigma = c.cfg->sigma, alpha = c.cfg->alpha, re = R.rho_eq;
+        VD t[C][3], tn[C][3], ru[C][2], r[C][3], xt[C][3];
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VD w0 = VD(re) * ze[j][0] - ye[j][0], w1 = VD(re) * ze[j][1] - ye[j][1], w2 = VD(re) * ze[j][2] - ye[j][2];
+            VD wb3 = c.ld(K_RHO + 3, j) * zb[j][3] - yb[j][3], wb4 = c.ld(K_RHO + 4, j) * zb[j][4] - yb[j][4];
+            VD b22 = c.ld(K_B + 0, j), b31 = c.ld(K_B + 1, j);
+            ru[j][0] = VD(sigma) * x[j][3] + c.ld(K_S + 3, j) * wb3 + b31 * w2 - c.ld(K_Q + 0, j);
+            ru[j][1] = VD(sigma) * x[j][4] + c.ld(K_S + 4, j) * wb4 + b22 * w1 - c.ld(K_Q + 1, j);
+            VD pv = c.ld(K_IV, j) * ru[j][0], pk = c.ld(K_IK, j) * ru[j][1];
+            t[j][0] = w0;
+            t[j][1] = w1 - c.ld(K_RB22, j) * pk;
+            t[j][2] = w2 - c.ld(K_RB31, j) * pv;
+        }
+        pull_next_raw<C, 3>(t, tn);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VD wb0 = c.ld(K_RHO + 0, j) * zb[j][0] - yb[j][0], wb1 = c.ld(K_RHO + 1, j) * zb[j][1] - yb[j][1],
+               wb2 = c.ld(K_RHO + 2, j) * zb[j][2] - yb[j][2];
+            r[j][0] = VD(sigma) * x[j][0] + c.ld(K_S + 0, j) * wb0 + c.ld(K_M + 0, j) * t[j][0] +
+                      (c.ld(K_A + 0, j) * tn[j][0] + c.ld(K_A + 2, j) * tn[j][1] + c.ld(K_A + 4, j) * tn[j][2]);
+            r[j][1] = VD(sigma) * x[j][1] + c.ld(K_S + 1, j) * wb1 + c.ld(K_M + 1, j) * t[j][1] +
+                      (c.ld(K_A + 1, j) * tn[j][0] + c.ld(K_A + 3, j) * tn[j][1]);
+            r[j][2] = VD(sigma) * x[j][2] + c.ld(K_S + 2, j) * wb2 + c.ld(K_M + 2, j) * t[j][2] +
+                      c.ld(K_A + 5, j) * tn[j][2];
+        }
+        block_solve(r, xt);
+        // p^ = A_s x~_s goes up to stage s+1
+        VD ph[C][3], cp[C][3];
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            ph[j][0] = c.ld(K_A + 0, j) * xt[j][0] + c.ld(K_A + 1, j) * xt[j][1];
+            ph[j][1] = c.ld(K_A + 2, j) * xt[j][0] + c.ld(K_A + 3, j) * xt[j][1];
+            ph[j][2] = c.ld(K_A + 4, j) * xt[j][0] + c.ld(K_A + 5, j) * xt[j][2];
+        }
+        pull_prev_rot<C, 3>(ph, cp);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VD e0 = c.ld(K_M + 0, j) * xt[j][0] + cp[j][0];
+            VD e1 = c.ld(K_M + 1, j) * xt[j][1] + cp[j][1];
+            VD e2 = c.ld(K_M + 2, j) * xt[j][2] + cp[j][2];
+            VD b22 = c.ld(K_B + 0, j), b31 = c.ld(K_B + 1, j);
+            VD utv = c.ld(K_IV, j) * (ru[j][0] - c.ld(K_RB31, j) * e2);
+            VD utk = c.ld(K_IK, j) * (ru[j][1] - c.ld(K_RB22, j) * e1);
+            VD zte[3] = {e0, e1 + b22 * utk, e2 + b31 * utv};
+            VD xv[5] = {xt[j][0], xt[j][1], xt[j][2], utv, utk};
+            // equality rows: l == u == b
+            for (int q = 0; q < 3; ++q) {
+                VD b = c.ld(K_BE + q, j);
+                VD zh = VD(alpha) * zte[q] + VD(1.0 - alpha) * ze[j][q];
+                VD zn = b;   // projection onto [b, b]
+                VD dy = VD(re) * (zh - zn);
+                ze[j][q] = zn;
+                ye[j][q] = ye[j][q] + dy;
+                dye[j][q] = dy;
+            }
+            for (int e = 0; e < 5; ++e) {
+                VD rho = c.ld(K_RHO + e, j), rinv = c.ld(K_RINV + e, j);
+                VD zt = c.ld(K_S + e, j) * xv[e];
+                VD zh = VD(alpha) * zt + VD(1.0 - alpha) * zb[j][e];
+                VD zn = vclamp(zh + rinv * yb[j][e], c.ld(K_LB + e, j), c.ld(K_UB + e, j));
+                VD dy = rho * (zh - zn);
+                zb[j][e] = zn;
+                yb[j][e] = yb[j][e] + dy;
+                dyb[j][e] = dy;
+                VD xn = VD(alpha) * xv[e] + VD(1.0 - alpha) * x[j][e];
+                if (keep_delta) dx[j][e] = xn - x[j][e];
+                x[j][e] = xn;
+            }
+        }
+    }
+
+    // A v on the equality rows owned by each stage (v: 5 local variables per stage)
+    AC_MEM void eq_rows(const VD (&v)[C][5], VD (&o)[C][3])
+    {
+        VD ph[C][3], cp[C][3];
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            ph[j][0] = c.ld(K_A + 0, j) * v[j][0] + c.ld(K_A + 1, j) * v[j][1];
+            ph[j][1] = c.ld(K_A + 2, j) * v[j][0] + c.ld(K_A + 3, j) * v[j][1];
+            ph[j][2] = c.ld(K_A + 4, j) * v[j][0] + c.ld(K_A + 5, j) * v[j][2];
+        }
+        pull_prev_k<C, 3>(ph, cp);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            o[j][0] = c.ld(K_M + 0, j) * v[j][0] + cp[j][0];
+            o[j][1] = c.ld(K_M + 1, j) * v[j][1] + cp[j][1] + c.ld(K_B + 0, j) * v[j][4];
+            o[j][2] = c.ld(K_M + 2, j) * v[j][2] + cp[j][2] + c.ld(K_B + 1, j) * v[j][3];
+        }
+    }
+    // A' (ve, vb) on the columns owned by each stage
+    AC_MEM void at_cols(const VD (&ve)[C][3], const VD (&vb)[C][5], VD (&o)[C][5])
+    {
+        VD vn[C][3];
+        pull_next_k<C, 3>(ve, vn);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            o[j][0] = c.ld(K_S + 0, j) * vb[j][0] + c.ld(K_M + 0, j) * ve[j][0] +
+                      (c.ld(K_A + 0, j) * vn[j][0] + c.ld(K_A + 2, j) * vn[j][1] + c.ld(K_A + 4, j) * vn[j][2]);
+            o[j][1] = c.ld(K_S + 1, j) * vb[j][1] + c.ld(K_M + 1, j) * ve[j][1] +
+                      (c.ld(K_A + 1, j) * vn[j][0] + c.ld(K_A + 3, j) * vn[j][1]);
+            o[j][2] = c.ld(K_S + 2, j) * vb[j][2] + c.ld(K_M + 2, j) * ve[j][2] + c.ld(K_A + 5, j) * vn[j][2];
+            o[j][3] = c.ld(K_S + 3, j) * vb[j][3] + c.ld(K_B + 1, j) * ve[j][2];
+            o[j][4] = c.ld(K_S + 4, j) * vb[j][4] + c.ld(K_B + 0, j) * ve[j][1];
+        }
+    }
+
+    AC_MEM void compute_norms(Norms& N)
+    {
+        VD v[12];
+        for (int t = 0; t < 12; ++t) v[t] = VD(0.0);
+        VD ax[C][3], aty[C][5];
+        eq_rows(x, ax);
+        at_cols(ye, yb, aty);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            for (int r = 0; r < 3; ++r) acc_row(v, ax[j][r], ze[j][r], c.ld(K_EEI + r, j));
+            for (int e = 0; e < 5; ++e) {
+                acc_row(v, c.ld(K_S + e, j) * x[j][e], zb[j][e], c.ld(K_EBI + e, j));
+                VD q = (e >= 3) ? c.ld(K_Q + e - 3, j) : VD(0.0);
+                acc_col(v, q, c.ld(K_P + e, j) * x[j][e], aty[j][e], c.ld(K_DI + e, j));
+            }
+        }
+        finish_norms(v, cinv, nq_unscaled, nq_scaled, N);
+    }
+
+    AC_MEM int primal_infeasible(double eps)
+    {
+        VD nrm = VD(0.0), lhs = VD(0.0);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            for (int r = 0; r < 3; ++r) {   // equality rows: finite bounds, no projection
+                VD b = c.ld(K_BE + r, j);
+                nrm = vmax(nrm, vabs(dye[j][r] / c.ld(K_EEI + r, j)));
+                lhs = lhs + support(dye[j][r], b, b);
+            }
+            for (int e = 0; e < 5; ++e) {
+                VD lo = c.ld(K_LB + e, j), hi = c.ld(K_UB + e, j);
+                dyb[j][e] = project_dy(dyb[j][e], lo, hi);
+                nrm = vmax(nrm, vabs(dyb[j][e] / c.ld(K_EBI + e, j)));
+                lhs = lhs + support(dyb[j][e], lo, hi);
+            }
+        }
+        double nr = wmax(nrm), lh = wsum(lhs);
+        if (uni(!(nr > eps) || !(lh < -eps * nr))) return 0;
+        VD aty[C][5], m = VD(0.0);
+        at_cols(dye, dyb, aty);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j)
+            for (int e = 0; e < 5; ++e) m = vmax(m, vabs(c.ld(K_DI + e, j) * aty[j][e]));
+        return wmax(m) < eps * nr;
+    }
+
+    AC_MEM int dual_infeasible(double eps)
+    {
+        VD nrm = VD(0.0), qdx = VD(0.0), pm = VD(0.0);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j)
+            for (int e = 0; e < 5; ++e) {
+                VD di = c.ld(K_DI + e, j);
+                nrm = vmax(nrm, vabs(dx[j][e] / di));
+                if (e >= 3) qdx = qdx + c.ld(K_Q + e - 3, j) * dx[j][e];
+                pm = vmax(pm, vabs(di * (c.ld(K_P + e, j) * dx[j][e])));
+            }
+        double nr = wmax(nrm), qd = wsum(qdx), pmx = wmax(pm);
+        if (uni(!(nr > eps) || !(qd < -cs * eps * nr) || !(pmx < cs * eps * nr))) return 0;
+        VD adx[C][3];
+        eq_rows(dx, adx);
+        VB bad = vb_all(false);
+        const VD lim = VD(eps * nr);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            for (int r = 0; r < 3; ++r) {   // equality rows: both bounds finite
+                VD a = adx[j][r] * c.ld(K_EEI + r, j);
+                bad = bad | (a > lim) | (a < -lim);
+            }
+            for (int e = 0; e < 5; ++e) {
+                VD a = c.ld(K_EBI + e, j) * (c.ld(K_S + e, j) * dx[j][e]);
+                VD lo = c.ld(K_LB + e, j), hi = c.ld(K_UB + e, j);
+                bad = bad | ((hi < VD(kBig)) & (a > lim)) | ((lo > VD(-kBig)) & (a < -lim));
+            }
+        }
+        return !wany(bad);
+    }
+
+    AC_MEM int check(const Norms& N, int approximate)
+    {
+        const acmpc_config& g = *c.cfg;
+        double k = approximate ? 10.0 : 1.0;
+        if (uni(N.pri > kInfty || N.dua > kInfty)) return ACMPC_NON_CVX;
+        double eps_p = k * g.eps_abs + k * g.eps_rel * fmax(N.nz, N.nAx);
+        double eps_d = k * g.eps_abs + k * g.eps_rel * cinv * fmax(N.nq, fmax(N.nAty, N.nPx));
+        int p_ok = uni(N.pri < eps_p), d_ok = uni(N.dua < eps_d);
+        int p_inf = 0, d_inf = 0;
+        if (!p_ok) p_inf = primal_infeasible(k * g.eps_prim_inf);
+        if (!d_ok) d_inf = dual_infeasible(k * g.eps_dual_inf);
+        if (p_ok && d_ok) return approximate ? ACMPC_SOLVED_INACCURATE : ACMPC_SOLVED;
+        if (p_inf) return approximate ? ACMPC_PRIMAL_INFEASIBLE_INACCURATE : ACMPC_PRIMAL_INFEASIBLE;
+        if (d_inf) return approximate ? ACMPC_DUAL_INFEASIBLE_INACCURATE : ACMPC_DUAL_INFEASIBLE;
+        return 0;
+    }
+
+    AC_MEM void solve(SolveInfo& info)
+    {
+        const acmpc_config& g = *c.cfg;
+        R.set(clampu(g.rho, kRhoMin, kRhoMax));
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            for (int e = 0; e < 5; ++e) x[j][e] = zb[j][e] = yb[j][e] = dx[j][e] = dyb[j][e] = VD(0.0);
+            for (int r = 0; r < 3; ++r) ye[j][r] = ze[j][r] = dye[j][r] = VD(0.0);
+        }
+        factor();
+        Norms N;
+        int status = 0, iter = 0, updates = 0;
+        for (;;) {
+            ++iter;
+            const bool checked = (g.check_termination > 0 && iter % g.check_termination == 0);
+            const bool last = iter >= g.max_iter;
+            const bool adapt = g.adaptive_rho && g.adaptive_rho_interval > 0 && iter % g.adaptive_rho_interval == 0;
+            iterate(checked || last);
+            if (checked || adapt || last) compute_norms(N);
+            // same two-phase structure as SpeedQP::solve
+            AC_NOUNROLL
+            for (int phase = 0; phase < 2 && !uni(status != 0); ++phase) {
+                if (phase == 0 ? checked : last) {
+                    const int lo = (phase == 1 && checked) ? 1 : 0;
+                    AC_NOUNROLL
+                    for (int approx = lo; approx <= phase && !uni(status != 0); ++approx) status = check(N, approx);
+                    if (phase == 1 && !status) status = ACMPC_MAX_ITER_REACHED;
+                }
+                if (phase == 0 && !uni(status != 0) && adapt) {
+                    double rn = rho_estimate(N, R.rho);
+                    if (uni(rn > R.rho * g.adaptive_rho_tolerance || rn < R.rho / g.adaptive_rho_tolerance)) {
+                        R.set(rn);
+                        ++updates;
+                        factor();
+                    }
+                }
+            }
+            if (uni(status != 0)) break;
+        }
+        info.status = status, info.iter = iter, info.rho_updates = updates;
+        info.pri_res = N.pri, info.dua_res = N.dua;
+        VD obj = VD(0.0);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j)
+            for (int e = 0; e < 5; ++e) {
+                VD xe = x[j][e];
+                obj = obj + VD(0.5) * c.ld(K_P + e, j) * xe * xe;
+                if (e >= 3) obj = obj + c.ld(K_Q + e - 3, j) * xe;
+            }
+        info.obj_val = final_obj(status, wsum(obj) * cinv);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// one full MPC step for one instance.  `raw_path` = (H,3) staged in shared memory (inside the scan
+// region: dead until the first control factorisation).
+// ------------------------------------------------------------------------------------------------
+struct InstanceOut {
+    double *controls, *prediction, *cum_time, *states, *v_ref, *cost, *pri_res, *dua_res;
+    int32_t *status, *status_speed, *iters, *rho_updates;
+    double* waypoints;
+};
+
+template <int C>
+AC_DEV void solve_instance(const Ctx<C>& c, const double* raw_path, double offset, double v_max_live,
+                           int localised, const InstanceOut& o)
+{
+    const int n = c.n, H = c.H;
+    PathRegs<C> path;
+    build_waypoints<C>(c, raw_path, path);
+    warp_sync();
+    SolveInfo si, ci;
+    VD vel[C];
+    {
+        SpeedQP<C> sq(c);
+        sq.assemble_and_scale(path, v_max_live, localised);
+        sq.solve(si, vel);
+        // spatial_mpc.py:115-122: velocities are assigned only when the status is "solved"
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) vel[j] = (si.status == ACMPC_SOLVED) ? vsel(vi_lt(c.stage(j), n), vel[j], VD(0.0)) : VD(0.0);
+    }
+    AC_UNROLL
+    for (int j = 0; j < C; ++j) {
+        VI st = c.stage(j);
+        VB ok = vi_lt(st, n);
+        c.st(F_XS, j, path.xs[j]), c.st(F_YS, j, path.ys[j]), c.st(F_PSI, j, path.psi[j]), c.st(F_VEL, j, vel[j]);
+        if (o.waypoints) {
+            st_idx_if(ok, o.waypoints + 0 * n, st, path.xs[j]);
+            st_idx_if(ok, o.waypoints + 1 * n, st, path.ys[j]);
+            st_idx_if(ok, o.waypoints + 2 * n, st, path.psi[j]);
+            st_idx_if(ok, o.waypoints + 3 * n, st, path.kap[j]);
+            st_idx_if(ok, o.waypoints + 4 * n, st, path.dist[j]);
+            st_idx_if(ok, o.waypoints + 5 * n, st, path.wid[j]);
+            st_idx_if(ok, o.waypoints + 6 * n, st, vel[j]);
+        }
+        if (o.v_ref) st_idx_if(ok, o.v_ref, st, vel[j]);
+    }
+    ControlQP<C> cq(c);
+    cq.setup(path, vel, offset);
+    cq.solve(ci);
+    // unpack (spatial_mpc.py:193-212) and roll out (dynamics.py:42-63)
+    const double L = c.cfg->wheelbase;
+    AC_UNROLL
+    for (int j = 0; j < C; ++j) {
+        VI st = c.stage(j);
+        VB isx = vi_lt(st, H), ok = vi_lt(st, n), hasU = vi_ge(st, 1) & isx;
+        VD ey = cq.x[j][0] / c.ld(K_DI + 0, j);
+        VD ep = cq.x[j][1] / c.ld(K_DI + 1, j);
+        VD tt = cq.x[j][2] / c.ld(K_DI + 2, j);
+        VD v = cq.x[j][3] / c.ld(K_DI + 3, j);
+        VD kc = cq.x[j][4] / c.ld(K_DI + 4, j);
+        if (o.states) {
+            st_idx_if(isx, o.states, st * 3, ey);
+            st_idx_if(isx, o.states, st * 3 + 1, ep);
+            st_idx_if(isx, o.states, st * 3 + 2, tt);
+        }
+        if (o.controls) {   // u_{s-1} lives with stage s
+            st_idx_if(hasU, o.controls, st + (-1), v);
+            st_idx_if(hasU, o.controls, st + (n - 1), vatan(kc * VD(L)));
+        }
+        if (o.prediction) {
+            VD ps = c.ld(F_PSI, j);
+            st_idx_if(ok, o.prediction, st * 2, c.ld(F_XS, j) - ey * vsin(ps));
+            st_idx_if(ok, o.prediction, st * 2 + 1, c.ld(F_YS, j) + ey * vcos(ps));
+        }
+        if (o.cum_time) st_idx_if(ok, o.cum_time, st, tt);
+    }
+    AC_LANE0
+    {
+        if (o.cost) *o.cost = ci.obj_val;
+        if (o.pri_res) *o.pri_res = ci.pri_res;
+        if (o.dua_res) *o.dua_res = ci.dua_res;
+        if (o.status) *o.status = ci.status;
+        if (o.status_speed) *o.status_speed = si.status;
+        if (o.iters) o.iters[0] = si.iter, o.iters[1] = ci.iter;
+        if (o.rho_updates) o.rho_updates[0] = si.rho_updates, o.rho_updates[1] = ci.rho_updates;
+    }
+}
+
+}  // namespace acmpc

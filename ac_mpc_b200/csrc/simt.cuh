@@ -1,0 +1,388 @@
+// simt.cuh -- the per-lane value types the kernel body is written in.
+//
+// nvcc (product build):  VD = double, VI = int, VB = bool -- one value per thread, shuffles are
+//                        __shfl_*_sync, reductions are xor butterflies.  Zero overhead.
+// g++ -DACMPC_EMULATE :  VD / VI / VB hold the values of all 32 lanes of a warp and every operation
+//                        is applied lane by lane, shuffles are permutations.  This lets the GPU-less
+//                        container execute the *same* warp-parallel algorithm (lane mapping, shuffles,
+//                        cyclic reductions) and compare it with the oracle (tests/_emul).  TEST ONLY:
+//                        it is never loaded by the package and is not a fallback.
+//
+// Rules the body follows so both builds mean the same thing: control flow depends on warp-uniform
+// values only (plain int/double/bool); per-lane conditions go through vsel(); memory is touched
+// through the ld_/st_ helpers below.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef ACMPC_EMULATE
+// ------------------------------------------------------------------------------------------------
+#define AC_DEV static inline
+#define AC_MEM inline
+#define AC_UNROLL
+#define AC_NOUNROLL
+#define AC_LANE0 if (true)
+#define AC_FOR_LANES for (int i_ = 0; i_ < 32; ++i_)
+
+namespace acmpc {
+
+struct VB {
+    bool v[32];
+};
+struct VI {
+    int v[32];
+};
+struct VD {
+    double v[32];
+    VD() {}
+    VD(double s) { AC_FOR_LANES v[i_] = s; }
+};
+
+#define AC_BIN(op)                                                         \
+    AC_DEV VD operator op(const VD& a, const VD& b)                        \
+    {                                                                      \
+        VD r;                                                              \
+        AC_FOR_LANES r.v[i_] = a.v[i_] op b.v[i_];                         \
+        return r;                                                          \
+    }
+AC_BIN(+) AC_BIN(-) AC_BIN(*) AC_BIN(/)
+#undef AC_BIN
+AC_DEV VD operator-(const VD& a)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = -a.v[i_];
+    return r;
+}
+AC_DEV VD& operator+=(VD& a, const VD& b) { return a = a + b; }
+AC_DEV VD& operator-=(VD& a, const VD& b) { return a = a - b; }
+AC_DEV VD& operator*=(VD& a, const VD& b) { return a = a * b; }
+
+#define AC_CMP(op)                                                         \
+    AC_DEV VB operator op(const VD& a, const VD& b)                        \
+    {                                                                      \
+        VB r;                                                              \
+        AC_FOR_LANES r.v[i_] = a.v[i_] op b.v[i_];                         \
+        return r;                                                          \
+    }
+AC_CMP(<) AC_CMP(>) AC_CMP(<=) AC_CMP(>=)
+#undef AC_CMP
+AC_DEV VB operator&(const VB& a, const VB& b)
+{
+    VB r;
+    AC_FOR_LANES r.v[i_] = a.v[i_] && b.v[i_];
+    return r;
+}
+AC_DEV VB operator|(const VB& a, const VB& b)
+{
+    VB r;
+    AC_FOR_LANES r.v[i_] = a.v[i_] || b.v[i_];
+    return r;
+}
+AC_DEV VB operator!(const VB& a)
+{
+    VB r;
+    AC_FOR_LANES r.v[i_] = !a.v[i_];
+    return r;
+}
+AC_DEV VB vb_all(bool s)
+{
+    VB r;
+    AC_FOR_LANES r.v[i_] = s;
+    return r;
+}
+
+AC_DEV VI lane_iota()
+{
+    VI r;
+    AC_FOR_LANES r.v[i_] = i_;
+    return r;
+}
+AC_DEV VI operator*(const VI& a, int b)
+{
+    VI r;
+    AC_FOR_LANES r.v[i_] = a.v[i_] * b;
+    return r;
+}
+AC_DEV VI operator+(const VI& a, int b)
+{
+    VI r;
+    AC_FOR_LANES r.v[i_] = a.v[i_] + b;
+    return r;
+}
+AC_DEV VI operator|(const VI& a, const VI& b)
+{
+    VI r;
+    AC_FOR_LANES r.v[i_] = a.v[i_] | b.v[i_];
+    return r;
+}
+AC_DEV VI operator<<(const VI& a, int b)
+{
+    VI r;
+    AC_FOR_LANES r.v[i_] = a.v[i_] << b;
+    return r;
+}
+AC_DEV VI vi_all(int s)
+{
+    VI r;
+    AC_FOR_LANES r.v[i_] = s;
+    return r;
+}
+// ((a >> sh) & 3) == which
+AC_DEV VB vi_field_is(const VI& a, int sh, int which)
+{
+    VB r;
+    AC_FOR_LANES r.v[i_] = ((a.v[i_] >> sh) & 3) == which;
+    return r;
+}
+#define AC_ICMP(name, op)                                                  \
+    AC_DEV VB name(const VI& a, int b)                                     \
+    {                                                                      \
+        VB r;                                                              \
+        AC_FOR_LANES r.v[i_] = a.v[i_] op b;                               \
+        return r;                                                          \
+    }
+AC_ICMP(vi_lt, <) AC_ICMP(vi_le, <=) AC_ICMP(vi_ge, >=) AC_ICMP(vi_eq, ==)
+#undef AC_ICMP
+
+AC_DEV VD vsel(const VB& m, const VD& a, const VD& b)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = m.v[i_] ? a.v[i_] : b.v[i_];
+    return r;
+}
+AC_DEV VI vseli(const VB& m, const VI& a, const VI& b)
+{
+    VI r;
+    AC_FOR_LANES r.v[i_] = m.v[i_] ? a.v[i_] : b.v[i_];
+    return r;
+}
+
+#define AC_UN(name, expr)                                                  \
+    AC_DEV VD name(const VD& a)                                            \
+    {                                                                      \
+        VD r;                                                              \
+        AC_FOR_LANES r.v[i_] = expr(a.v[i_]);                              \
+        return r;                                                          \
+    }
+AC_UN(vabs, fabs) AC_UN(vsqrt, sqrt) AC_UN(vsin, sin) AC_UN(vcos, cos) AC_UN(vatan, atan)
+#undef AC_UN
+AC_DEV VD vmax(const VD& a, const VD& b)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = fmax(a.v[i_], b.v[i_]);
+    return r;
+}
+AC_DEV VD vmin(const VD& a, const VD& b)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = fmin(a.v[i_], b.v[i_]);
+    return r;
+}
+AC_DEV VD vatan2(const VD& y, const VD& x)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = atan2(y.v[i_], x.v[i_]);
+    return r;
+}
+AC_DEV VD vfmod(const VD& a, double b)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = fmod(a.v[i_], b);
+    return r;
+}
+
+// shuffles: out-of-range sources deliver 0 (the "0" variants) or the lane's own value
+AC_DEV VD shfl_up0(const VD& a, int d)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = (i_ >= d) ? a.v[i_ - d] : 0.0;
+    return r;
+}
+AC_DEV VD shfl_down0(const VD& a, int d)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = (i_ + d < 32) ? a.v[i_ + d] : 0.0;
+    return r;
+}
+AC_DEV VD shfl_idx(const VD& a, int src)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = a.v[src];
+    return r;
+}
+// "raw" shuffles: an out-of-range source delivers the lane's OWN value (the hardware behaviour); callers
+// multiply the result by a coefficient that is zero on those lanes
+AC_DEV VD shfl_up_raw(const VD& a, int d)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = (i_ >= d) ? a.v[i_ - d] : a.v[i_];
+    return r;
+}
+AC_DEV VD shfl_down_raw(const VD& a, int d)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = (i_ + d < 32) ? a.v[i_ + d] : a.v[i_];
+    return r;
+}
+// value of lane-1, lane 0 takes lane 31's (rotation)
+AC_DEV VD shfl_rot_up1(const VD& a)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = a.v[(i_ + 31) & 31];
+    return r;
+}
+// warp-uniform predicate (all lanes hold the same value; the device build tells the compiler so)
+AC_DEV bool uni(bool p) { return p; }
+AC_DEV VD vrsqrt(const VD& a)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = 1.0 / sqrt(a.v[i_]);
+    return r;
+}
+AC_DEV double lane_value(const VD& a, int src) { return a.v[src]; }
+
+// warp reductions (same xor-butterfly order as the device build); result is warp-uniform
+AC_DEV double wmax(const VD& a)
+{
+    VD t = a;
+    for (int o = 16; o > 0; o >>= 1) {
+        VD u;
+        AC_FOR_LANES u.v[i_] = fmax(t.v[i_], t.v[i_ ^ o]);
+        t = u;
+    }
+    return t.v[0];
+}
+AC_DEV double wsum(const VD& a)
+{
+    VD t = a;
+    for (int o = 16; o > 0; o >>= 1) {
+        VD u;
+        AC_FOR_LANES u.v[i_] = t.v[i_] + t.v[i_ ^ o];
+        t = u;
+    }
+    return t.v[0];
+}
+AC_DEV bool wany(const VB& a)
+{
+    bool r = false;
+    AC_FOR_LANES r = r || a.v[i_];
+    return r;
+}
+
+// memory: base[lane], base[idx], predicated stores
+AC_DEV VD ld_lane(const double* base)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = base[i_];
+    return r;
+}
+AC_DEV void st_lane(double* base, const VD& a) { AC_FOR_LANES base[i_] = a.v[i_]; }
+AC_DEV VD ld_idx_if(const VB& m, const double* base, const VI& idx, double other)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = m.v[i_] ? base[idx.v[i_]] : other;
+    return r;
+}
+AC_DEV void st_idx_if(const VB& m, double* base, const VI& idx, const VD& a)
+{
+    AC_FOR_LANES if (m.v[i_]) base[idx.v[i_]] = a.v[i_];
+}
+// base[min(lane + off, 31)]: the slot of the lane `off` places up, clamped (callers multiply the
+// clamped reads by a shuffled-in zero)
+AC_DEV VD ld_lane_at(const double* base, int off)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = base[(i_ + off < 32) ? i_ + off : 31];
+    return r;
+}
+AC_DEV VB vb_not(const VB& a) { return !a; }
+AC_DEV void warp_sync() {}
+
+}  // namespace acmpc
+
+#else
+// ------------------------------------------------------------------------------------------------
+#define AC_DEV __device__ __forceinline__
+#define AC_MEM __device__ __forceinline__
+#define AC_UNROLL _Pragma("unroll")
+#define AC_NOUNROLL _Pragma("unroll 1")
+#define AC_LANE0 if ((threadIdx.x & 31) == 0)
+
+namespace acmpc {
+
+using VD = double;
+using VI = int;
+using VB = bool;
+
+constexpr unsigned kFull = 0xffffffffu;
+
+AC_DEV VB vb_all(bool s) { return s; }
+AC_DEV VI lane_iota() { return (int)(threadIdx.x & 31); }
+AC_DEV VI vi_all(int s) { return s; }
+AC_DEV VB vi_field_is(VI a, int sh, int which) { return ((a >> sh) & 3) == which; }
+AC_DEV VB vi_lt(VI a, int b) { return a < b; }
+AC_DEV VB vi_le(VI a, int b) { return a <= b; }
+AC_DEV VB vi_ge(VI a, int b) { return a >= b; }
+AC_DEV VB vi_eq(VI a, int b) { return a == b; }
+AC_DEV VD vsel(bool m, double a, double b) { return m ? a : b; }
+AC_DEV VI vseli(bool m, int a, int b) { return m ? a : b; }
+AC_DEV VD vabs(double a) { return fabs(a); }
+AC_DEV VD vsqrt(double a) { return sqrt(a); }
+AC_DEV VD vsin(double a) { return sin(a); }
+AC_DEV VD vcos(double a) { return cos(a); }
+AC_DEV VD vatan(double a) { return atan(a); }
+AC_DEV VD vmax(double a, double b) { return fmax(a, b); }
+AC_DEV VD vmin(double a, double b) { return fmin(a, b); }
+AC_DEV VD vatan2(double y, double x) { return atan2(y, x); }
+AC_DEV VD vfmod(double a, double b) { return fmod(a, b); }
+
+AC_DEV VD shfl_up0(double a, int d)
+{
+    double t = __shfl_up_sync(kFull, a, d);
+    return ((int)(threadIdx.x & 31) >= d) ? t : 0.0;
+}
+AC_DEV VD shfl_down0(double a, int d)
+{
+    double t = __shfl_down_sync(kFull, a, d);
+    return ((int)(threadIdx.x & 31) + d < 32) ? t : 0.0;
+}
+AC_DEV VD shfl_idx(double a, int src) { return __shfl_sync(kFull, a, src); }
+AC_DEV VD shfl_up_raw(double a, int d) { return __shfl_up_sync(kFull, a, d); }
+AC_DEV VD shfl_down_raw(double a, int d) { return __shfl_down_sync(kFull, a, d); }
+AC_DEV VD shfl_rot_up1(double a) { return __shfl_sync(kFull, a, ((int)(threadIdx.x & 31) + 31) & 31); }
+AC_DEV bool uni(bool p) { return __any_sync(kFull, p) != 0; }
+AC_DEV VD vrsqrt(double a) { return rsqrt(a); }
+AC_DEV double lane_value(double a, int src) { return __shfl_sync(kFull, a, src); }
+
+AC_DEV double wmax(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+AC_DEV double wsum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+AC_DEV bool wany(bool p) { return __any_sync(kFull, p) != 0; }
+
+AC_DEV VD ld_lane(const double* base) { return base[threadIdx.x & 31]; }
+AC_DEV void st_lane(double* base, double a) { base[threadIdx.x & 31] = a; }
+AC_DEV VD ld_idx_if(bool m, const double* base, int idx, double other) { return m ? base[idx] : other; }
+AC_DEV void st_idx_if(bool m, double* base, int idx, double a)
+{
+    if (m) base[idx] = a;
+}
+AC_DEV VD ld_lane_at(const double* base, int off)
+{
+    int i = (int)(threadIdx.x & 31) + off;
+    return base[i < 32 ? i : 31];
+}
+AC_DEV VB vb_not(bool a) { return !a; }
+AC_DEV void warp_sync() { __syncwarp(); }
+
+}  // namespace acmpc
+#endif

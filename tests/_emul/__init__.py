@@ -16,7 +16,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(_HERE, "emul.cpp"), os.path.join(_ROOT, "ac_mpc_b200", "csrc", "mpc_body.cuh"),
+        srcs = [os.path.join(_HERE, "emul.cpp"), os.path.join(_ROOT, "ac_mpc_b200", "csrc", "mpc_warp.cuh"), os.path.join(_ROOT, "ac_mpc_b200", "csrc", "simt.cuh"),
                 os.path.join(_ROOT, "include", "acmpc_b200.h")]
         if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
             subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", "-o", _SO, srcs[0]],

@@ -1,29 +1,29 @@
-// tests/_emul/emul.cpp -- TEST-ONLY one-lane CPU emulation of the kernel body.
+// tests/_emul/emul.cpp -- TEST-ONLY 32-lane lock-step CPU emulation of the kernel body.
 //
-// Compiles ac_mpc_b200/csrc/mpc_body.cuh with -DACMPC_EMULATE (ACMPC_LANES == 1, no shuffles, no
-// barriers) so the arithmetic of the CUDA path can be debugged in a GPU-less container against the
-// oracle.  It is NOT part of the product: the package never loads it, the C ABI does not expose it,
-// and it proves nothing about the parallel execution (that is what the -m gpu tests are for).
+// Compiles ac_mpc_b200/csrc/mpc_warp.cuh with -DACMPC_EMULATE: the per-lane value types of simt.cuh
+// become 32-wide arrays and every shuffle / reduction is applied lane by lane, so the SAME warp-parallel
+// algorithm (lane ownership, shuffles, scans) runs in a GPU-less container and can be compared with the
+// oracle.  It is NOT part of the product: the package never loads it and the C ABI does not expose it.
 #define ACMPC_EMULATE 1
-#include "../../ac_mpc_b200/csrc/mpc_body.cuh"
+#include "../../ac_mpc_b200/csrc/mpc_warp.cuh"
 
 #include <stdlib.h>
 #include <string.h>
 
-extern "C" int acmpc_emul_smem_doubles(int H) { return acmpc::smem_doubles(H); }
+namespace {
 
-extern "C" int acmpc_emul_solve_batch(const acmpc_config* cfg, int B, const double* paths,
-                                      const double* offsets, const double* vmax, int is_localised,
-                                      const acmpc_outputs* out)
+template <int C>
+void run(const acmpc_config* cfg, int B, const double* paths, const double* offsets, const double* vmax,
+         int is_localised, const acmpc_outputs* out)
 {
     const int H = cfg->horizon, n = H - 1;
-    if (H < ACMPC_MIN_HORIZON || H > ACMPC_MAX_HORIZON) return ACMPC_ERR_INVALID;
-    double* smem = (double*)malloc(sizeof(double) * (size_t)acmpc::smem_doubles(H));
+    const size_t nd = (size_t)acmpc::smem_doubles<C>();
+    double* smem = (double*)malloc(sizeof(double) * nd);
     for (int b = 0; b < B; ++b) {
-        memset(smem, 0xff, sizeof(double) * (size_t)acmpc::smem_doubles(H));  // NaN-poison
-        acmpc::Ctx c;
-        c.S = smem, c.H = H, c.n = n, c.Hs = H, c.lane = 0, c.cfg = cfg;
-        double* raw = c.f(acmpc::F_PATH_END);
+        memset(smem, 0xff, sizeof(double) * nd);   // NaN-poison
+        acmpc::Ctx<C> c;
+        c.S = smem, c.H = H, c.n = n, c.cfg = cfg, c.lane = acmpc::lane_iota();
+        double* raw = c.scan(0, 0);
         memcpy(raw, paths + (size_t)b * 3 * H, sizeof(double) * 3 * (size_t)H);
         acmpc::InstanceOut o;
         o.controls = out->controls ? out->controls + (size_t)b * 2 * n : nullptr;
@@ -39,9 +39,24 @@ extern "C" int acmpc_emul_solve_batch(const acmpc_config* cfg, int B, const doub
         o.iters = out->iters ? out->iters + (size_t)b * 2 : nullptr;
         o.rho_updates = out->rho_updates ? out->rho_updates + (size_t)b * 2 : nullptr;
         o.waypoints = out->waypoints ? out->waypoints + (size_t)b * 7 * n : nullptr;
-        acmpc::solve_instance(c, raw, offsets ? offsets[b] : 0.0, vmax ? vmax[b] : cfg->v_max,
-                              is_localised, o);
+        acmpc::solve_instance<C>(c, raw, offsets ? offsets[b] : 0.0, vmax ? vmax[b] : cfg->v_max, is_localised, o);
     }
     free(smem);
+}
+
+}  // namespace
+
+extern "C" int acmpc_emul_solve_batch(const acmpc_config* cfg, int B, const double* paths,
+                                      const double* offsets, const double* vmax, int is_localised,
+                                      const acmpc_outputs* out)
+{
+    const int H = cfg->horizon;
+    if (H < ACMPC_MIN_HORIZON || H > ACMPC_MAX_HORIZON) return ACMPC_ERR_INVALID;
+    switch ((H + 31) / 32) {
+        case 1: run<1>(cfg, B, paths, offsets, vmax, is_localised, out); break;
+        case 2: run<2>(cfg, B, paths, offsets, vmax, is_localised, out); break;
+        case 3: run<3>(cfg, B, paths, offsets, vmax, is_localised, out); break;
+        default: run<4>(cfg, B, paths, offsets, vmax, is_localised, out); break;
+    }
     return 0;
 }
