@@ -236,6 +236,23 @@ AC_DEV void pull_prev(const VD (&v)[C], VD (&o)[C])
     for (int j = C - 1; j >= 1; --j) o[j] = v[j - 1];
     o[0] = pv;
 }
+// scalar hot-loop variants (see pull_next_raw / pull_prev_rot below)
+template <int C>
+AC_DEV void pull_next_raw1(const VD (&v)[C], VD (&o)[C])
+{
+    VD nx = shfl_down_raw(v[0], 1);
+    AC_UNROLL
+    for (int j = 0; j + 1 < C; ++j) o[j] = v[j + 1];
+    o[C - 1] = nx;
+}
+template <int C>
+AC_DEV void pull_prev_rot1(const VD (&v)[C], VD (&o)[C])
+{
+    VD pv = shfl_rot_up1(v[C - 1]);
+    AC_UNROLL
+    for (int j = C - 1; j >= 1; --j) o[j] = v[j - 1];
+    o[0] = pv;
+}
 template <int C, int K>
 AC_DEV void pull_next_k(const VD (&v)[C][K], VD (&o)[C][K])
 {
@@ -605,6 +622,47 @@ struct SpeedQP {
         return 0;
     }
 
+    // one ADMM iteration (osqp_solve loop body)
+    AC_MEM void iterate(const double alpha, const double sigma)
+    {
+        VD r[C], xt[C], xn[C], t[C], tp[C];
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VD wa = rho_a[j] * za[j] - ya[j];
+            t[j] = au[j] * wa;
+            r[j] = VD(sigma) * x[j] - q[j] + ss[j] * (rho_b[j] * zb[j] - yb[j]) + al[j] * wa;
+        }
+        pull_prev_rot1<C>(t, tp);   // au = 0 on the last stage: lane 0 pulls a zero
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) r[j] = r[j] + tp[j];
+        kkt_solve(r, xt);
+        pull_next_raw1<C>(xt, xn);   // multiplied by au = 0 beyond the last row
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            {
+                VD zt = al[j] * xt[j] + au[j] * xn[j];
+                VD zh = VD(alpha) * zt + VD(1.0 - alpha) * za[j];
+                VD zn = vclamp(zh + rinv_a[j] * ya[j], la[j], ua[j]);
+                VD dy = rho_a[j] * (zh - zn);
+                za[j] = zn;
+                ya[j] = ya[j] + dy;
+                dya[j] = dy;
+            }
+            {
+                VD zt = ss[j] * xt[j];
+                VD zh = VD(alpha) * zt + VD(1.0 - alpha) * zb[j];
+                VD zn = vclamp(zh + rinv_b[j] * yb[j], lb[j], ub[j]);
+                VD dy = rho_b[j] * (zh - zn);
+                zb[j] = zn;
+                yb[j] = yb[j] + dy;
+                dyb[j] = dy;
+            }
+            VD xnew = VD(alpha) * xt[j] + VD(1.0 - alpha) * x[j];
+            dx[j] = xnew - x[j];
+            x[j] = xnew;
+        }
+    }
+
     // osqp_solve, cold start.  Result (unscaled v) -> vout.
     AC_MEM void solve(SolveInfo& info, VD (&vout)[C])
     {
@@ -619,60 +677,26 @@ struct SpeedQP {
         factor();
         Norms N;
         int status = 0, iter = 0, updates = 0;
+        // osqp_solve's order: iterate -> exact check (every check_termination iterations) -> adaptive rho;
+        // at the iteration limit the exact check if it has not just run, then the 10x "inaccurate" one.
+        // `pass` 0 is an ADMM iteration, passes 1 and 2 are those two extra checks: check() has ONE call site.
+        int pass = 0;
+        bool checked = false, adapt = false, last = false;
         for (;;) {
-            ++iter;
-            VD r[C], xt[C], xn[C], t[C], tp[C];
-            AC_UNROLL
-            for (int j = 0; j < C; ++j) {
-                VD wa = rho_a[j] * za[j] - ya[j];
-                t[j] = au[j] * wa;
-                r[j] = VD(sigma) * x[j] - q[j] + ss[j] * (rho_b[j] * zb[j] - yb[j]) + al[j] * wa;
+            if (pass == 0) {
+                ++iter;
+                checked = (g.check_termination > 0 && iter % g.check_termination == 0);
+                last = iter >= g.max_iter;
+                adapt = g.adaptive_rho && g.adaptive_rho_interval > 0 && iter % g.adaptive_rho_interval == 0;
+                iterate(alpha, sigma);
+                if (checked || adapt || last) compute_norms(N);
             }
-            pull_prev<C>(t, tp);
-            AC_UNROLL
-            for (int j = 0; j < C; ++j) r[j] = r[j] + tp[j];
-            kkt_solve(r, xt);
-            pull_next<C>(xt, xn);
-            const bool checked = (g.check_termination > 0 && iter % g.check_termination == 0);
-            const bool last = iter >= g.max_iter;
-            AC_UNROLL
-            for (int j = 0; j < C; ++j) {
-                {
-                    VD zt = al[j] * xt[j] + au[j] * xn[j];
-                    VD zh = VD(alpha) * zt + VD(1.0 - alpha) * za[j];
-                    VD zn = vclamp(zh + rinv_a[j] * ya[j], la[j], ua[j]);
-                    VD dy = rho_a[j] * (zh - zn);
-                    za[j] = zn;
-                    ya[j] = ya[j] + dy;
-                    dya[j] = dy;
-                }
-                {
-                    VD zt = ss[j] * xt[j];
-                    VD zh = VD(alpha) * zt + VD(1.0 - alpha) * zb[j];
-                    VD zn = vclamp(zh + rinv_b[j] * yb[j], lb[j], ub[j]);
-                    VD dy = rho_b[j] * (zh - zn);
-                    zb[j] = zn;
-                    yb[j] = yb[j] + dy;
-                    dyb[j] = dy;
-                }
-                VD xnew = VD(alpha) * xt[j] + VD(1.0 - alpha) * x[j];
-                dx[j] = xnew - x[j];
-                x[j] = xnew;
+            if (pass > 0 || checked) {
+                status = check(N, pass == 2);
+                if (uni(status != 0)) break;
             }
-            const bool adapt = g.adaptive_rho && g.adaptive_rho_interval > 0 && iter % g.adaptive_rho_interval == 0;
-            if (checked || adapt || last) compute_norms(N);
-            // osqp_solve's order: exact check (every check_termination iterations) -> adaptive rho ->
-            // at the iteration limit the exact check if it has not just run, then the 10x "inaccurate" one.
-            // Written as a two-phase loop so that check()/factor() are inlined once.
-            AC_NOUNROLL
-            for (int phase = 0; phase < 2 && !uni(status != 0); ++phase) {
-                if (phase == 0 ? checked : last) {
-                    const int lo = (phase == 1 && checked) ? 1 : 0;
-                    AC_NOUNROLL
-                    for (int approx = lo; approx <= phase && !uni(status != 0); ++approx) status = check(N, approx);
-                    if (phase == 1 && !status) status = ACMPC_MAX_ITER_REACHED;
-                }
-                if (phase == 0 && !uni(status != 0) && adapt) {
+            if (pass == 0) {
+                if (adapt) {
                     double rn = rho_estimate(N, R.rho);
                     if (uni(rn > R.rho * g.adaptive_rho_tolerance || rn < R.rho / g.adaptive_rho_tolerance)) {
                         R.set(rn);
@@ -680,8 +704,13 @@ struct SpeedQP {
                         factor();
                     }
                 }
+                if (last) pass = checked ? 2 : 1;
+            } else if (pass == 1) {
+                pass = 2;
+            } else {
+                status = ACMPC_MAX_ITER_REACHED;
+                break;
             }
-            if (uni(status != 0)) break;
         }
         info.status = status, info.iter = iter, info.rho_updates = updates;
         info.pri_res = N.pri, info.dua_res = N.dua;
@@ -1309,23 +1338,24 @@ struct ControlQP {
         factor();
         Norms N;
         int status = 0, iter = 0, updates = 0;
+        // same pass structure as SpeedQP::solve
+        int pass = 0;
+        bool checked = false, adapt = false, last = false;
         for (;;) {
-            ++iter;
-            const bool checked = (g.check_termination > 0 && iter % g.check_termination == 0);
-            const bool last = iter >= g.max_iter;
-            const bool adapt = g.adaptive_rho && g.adaptive_rho_interval > 0 && iter % g.adaptive_rho_interval == 0;
-            iterate(checked || last);
-            if (checked || adapt || last) compute_norms(N);
-            // same two-phase structure as SpeedQP::solve
-            AC_NOUNROLL
-            for (int phase = 0; phase < 2 && !uni(status != 0); ++phase) {
-                if (phase == 0 ? checked : last) {
-                    const int lo = (phase == 1 && checked) ? 1 : 0;
-                    AC_NOUNROLL
-                    for (int approx = lo; approx <= phase && !uni(status != 0); ++approx) status = check(N, approx);
-                    if (phase == 1 && !status) status = ACMPC_MAX_ITER_REACHED;
-                }
-                if (phase == 0 && !uni(status != 0) && adapt) {
+            if (pass == 0) {
+                ++iter;
+                checked = (g.check_termination > 0 && iter % g.check_termination == 0);
+                last = iter >= g.max_iter;
+                adapt = g.adaptive_rho && g.adaptive_rho_interval > 0 && iter % g.adaptive_rho_interval == 0;
+                iterate(checked || last);
+                if (checked || adapt || last) compute_norms(N);
+            }
+            if (pass > 0 || checked) {
+                status = check(N, pass == 2);
+                if (uni(status != 0)) break;
+            }
+            if (pass == 0) {
+                if (adapt) {
                     double rn = rho_estimate(N, R.rho);
                     if (uni(rn > R.rho * g.adaptive_rho_tolerance || rn < R.rho / g.adaptive_rho_tolerance)) {
                         R.set(rn);
@@ -1333,8 +1363,13 @@ struct ControlQP {
                         factor();
                     }
                 }
+                if (last) pass = checked ? 2 : 1;
+            } else if (pass == 1) {
+                pass = 2;
+            } else {
+                status = ACMPC_MAX_ITER_REACHED;
+                break;
             }
-            if (uni(status != 0)) break;
         }
         info.status = status, info.iter = iter, info.rho_updates = updates;
         info.pri_res = N.pri, info.dua_res = N.dua;
