@@ -1,9 +1,10 @@
 // acmpc_b200.cu -- sm_100a kernel + C ABI (include/acmpc_b200.h) of the batched MPC step.
 //
-// One warp (one CTA of 32 threads) owns one problem instance; its (H,3) reference-path slice is
-// staged into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier), everything else
-// (waypoints, both QPs, ADMM iterates, factorisations) stays in that CTA's registers and shared memory
-// until the results are written back.  The per-instance algorithm is in mpc_warp.cuh; the kernel is
+// One warp owns one problem instance (four warps = four instances per CTA); its (H,3) reference-path
+// slice is staged into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier), everything else
+// (waypoints, both QPs, ADMM iterates, factorisations) stays in that warp's registers, its quarter of the
+// CTA's TENSOR MEMORY allocation (used as a lane-private FP64 scratchpad through tcgen05.ld/st) and its
+// slice of shared memory until the results are written back.  The per-instance algorithm is in mpc_warp.cuh; the kernel is
 // instantiated for C = ceil(H/32) = 1..4 horizon stages per lane.
 //
 // There is NO CPU path in this library: acmpc_create fails with ACMPC_ERR_NO_DEVICE without a GPU.
@@ -63,44 +64,72 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
     }
 }
 
+constexpr int kWarpsPerCta = 4;   // one instance per warp; four warps share one tensor-memory allocation
+
 template <int C>
-__global__ void __launch_bounds__(32) acmpc_step_kernel(const __grid_constant__ KernelParams p)
+__host__ __device__ constexpr size_t warp_smem_bytes()
+{
+    return sizeof(double) * (size_t)acmpc::Layout<C>::kDoubles + 16;   // + the warp's TMA mbarrier
+}
+
+template <int C>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C == 2 ? 2 : 1)))
+    acmpc_step_kernel(const __grid_constant__ KernelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int b = blockIdx.x;
-    const int lane = threadIdx.x;
-    const int H = p.cfg.horizon, n = H - 1;
-    acmpc::Ctx<C> c;
-    c.S = reinterpret_cast<double*>(smem_raw);
-    c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(c.S + acmpc::Layout<C>::kDoubles);
-    // the raw path slice lands in the scan-matrix region: it is dead before the first control factorisation
-    double* raw = c.scan(0, 0);
-    const double* src = p.paths + (size_t)b * 3 * H;
-    if (p.use_tma) {
-        tma_load_1d(raw, src, (uint32_t)(3 * H * sizeof(double)), mbar, lane);
-    } else {
-        for (int i = lane; i < 3 * H; i += 32) raw[i] = src[i];
-        __syncwarp();
+    __shared__ uint32_t tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kWarpsPerCta + warp;
+    // tensor memory: warp 0 allocates the CTA's columns, every warp then owns its 32-lane quarter of them
+    constexpr uint32_t kCols = acmpc::Layout<C>::kTmemCols;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)),
+                     "n"(kCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    acmpc::InstanceOut o;
-    const acmpc_outputs& g = p.out;
-    o.controls = g.controls ? g.controls + (size_t)b * 2 * n : nullptr;
-    o.prediction = g.prediction ? g.prediction + (size_t)b * 2 * n : nullptr;
-    o.cum_time = g.cum_time ? g.cum_time + (size_t)b * n : nullptr;
-    o.states = g.states ? g.states + (size_t)b * 3 * H : nullptr;
-    o.v_ref = g.v_ref ? g.v_ref + (size_t)b * n : nullptr;
-    o.cost = g.cost ? g.cost + b : nullptr;
-    o.pri_res = g.pri_res ? g.pri_res + b : nullptr;
-    o.dua_res = g.dua_res ? g.dua_res + b : nullptr;
-    o.status = g.status ? g.status + b : nullptr;
-    o.status_speed = g.status_speed ? g.status_speed + b : nullptr;
-    o.iters = g.iters ? g.iters + (size_t)b * 2 : nullptr;
-    o.rho_updates = g.rho_updates ? g.rho_updates + (size_t)b * 2 : nullptr;
-    o.waypoints = g.waypoints ? g.waypoints + (size_t)b * 7 * n : nullptr;
-    const double offset = p.offsets ? p.offsets[b] : 0.0;
-    const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
-    acmpc::solve_instance<C>(c, raw, offset, vmax, p.is_localised, o);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (b < p.B) {
+        const int H = p.cfg.horizon, n = H - 1;
+        acmpc::Ctx<C> c;
+        c.S = reinterpret_cast<double*>(smem_raw + (size_t)warp * warp_smem_bytes<C>());
+        c.tm.a = tmem_base + ((uint32_t)(32 * warp) << 16);
+        c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
+        uint64_t* mbar = reinterpret_cast<uint64_t*>(c.S + acmpc::Layout<C>::kDoubles);
+        // the raw path slice lands in the scratch region: it is dead before the first factorisation
+        double* raw = c.scratch();
+        const double* src = p.paths + (size_t)b * 3 * H;
+        if (p.use_tma) {
+            tma_load_1d(raw, src, (uint32_t)(3 * H * sizeof(double)), mbar, lane);
+        } else {
+            for (int i = lane; i < 3 * H; i += 32) raw[i] = src[i];
+            __syncwarp();
+        }
+        acmpc::InstanceOut o;
+        const acmpc_outputs& g = p.out;
+        o.controls = g.controls ? g.controls + (size_t)b * 2 * n : nullptr;
+        o.prediction = g.prediction ? g.prediction + (size_t)b * 2 * n : nullptr;
+        o.cum_time = g.cum_time ? g.cum_time + (size_t)b * n : nullptr;
+        o.states = g.states ? g.states + (size_t)b * 3 * H : nullptr;
+        o.v_ref = g.v_ref ? g.v_ref + (size_t)b * n : nullptr;
+        o.cost = g.cost ? g.cost + b : nullptr;
+        o.pri_res = g.pri_res ? g.pri_res + b : nullptr;
+        o.dua_res = g.dua_res ? g.dua_res + b : nullptr;
+        o.status = g.status ? g.status + b : nullptr;
+        o.status_speed = g.status_speed ? g.status_speed + b : nullptr;
+        o.iters = g.iters ? g.iters + (size_t)b * 2 : nullptr;
+        o.rho_updates = g.rho_updates ? g.rho_updates + (size_t)b * 2 : nullptr;
+        o.waypoints = g.waypoints ? g.waypoints + (size_t)b * 7 * n : nullptr;
+        const double offset = p.offsets ? p.offsets[b] : 0.0;
+        const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
+        acmpc::solve_instance<C>(c, raw, offset, vmax, p.is_localised, o);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
 }
 
 // FP64 FMA throughput probe: 8 independent chains per thread, no memory traffic.
@@ -165,16 +194,14 @@ bool valid_config(const acmpc_config* c, std::string* why)
 
 int stages_per_lane(int H) { return (H + 31) / 32; }
 
-size_t smem_bytes_for(int H)
+size_t smem_bytes_for(int H)   // dynamic shared memory per CTA
 {
-    size_t d = 0;
     switch (stages_per_lane(H)) {
-        case 1: d = acmpc::smem_doubles<1>(); break;
-        case 2: d = acmpc::smem_doubles<2>(); break;
-        case 3: d = acmpc::smem_doubles<3>(); break;
-        default: d = acmpc::smem_doubles<4>(); break;
+        case 1: return kWarpsPerCta * warp_smem_bytes<1>();
+        case 2: return kWarpsPerCta * warp_smem_bytes<2>();
+        case 3: return kWarpsPerCta * warp_smem_bytes<3>();
+        default: return kWarpsPerCta * warp_smem_bytes<4>();
     }
-    return sizeof(double) * d + 16;
 }
 
 const void* kernel_for(int H)
@@ -201,9 +228,10 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     p.use_tma = ((3 * H * sizeof(double)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_paths) & 15) == 0);
     const size_t smem = smem_bytes_for(H);
     void* args[] = {&p};
-    if (fail(h, cudaLaunchKernel(kernel_for(H), dim3(B), dim3(32), args, smem, stream), "kernel launch"))
+    const int ctas = (B + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (fail(h, cudaLaunchKernel(kernel_for(H), dim3(ctas), dim3(32 * kWarpsPerCta), args, smem, stream), "kernel launch"))
         return ACMPC_ERR_CUDA;
-    h->last_launches = 1, h->last_smem = (int)smem, h->last_threads = 32, h->last_ipc = 1;
+    h->last_launches = 1, h->last_smem = (int)smem, h->last_threads = 32 * kWarpsPerCta, h->last_ipc = kWarpsPerCta;
     if (fail(h, cudaGetLastError(), "kernel launch")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
 }

@@ -49,34 +49,48 @@ constexpr double kPi = 3.14159265358979323846;
 constexpr int kLevels = 5;                      // Kogge-Stone levels over 32 lanes
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory map.  Per-stage field f of stage (lane, j) is S[(f*C + j)*32 + lane].
+// On-chip data map of one instance (one warp).
+//
+// TENSOR MEMORY (lane private, 64 doubles = 128 columns per stage; stage (lane, j) of the instance starts
+// at double column j*64 of the lane's row).  Everything the ADMM iteration reads every time lives here and
+// is fetched as 16-double chunks (one tcgen05.ld.32x32b.x32 each):
+//   chunk F  [ 0,16)  rho[5] rinv[5] iv ik rb31 rb22 - -        rewritten by every factorisation
+//   chunk G  [16,32)  s[5] m[3] b22 b31 a11 a12 a21 a22 a31 a33 scaled constraint matrix
+//   chunk H  [32,48)  q[2] be[3] lb[5] ub[5] -                  scaled cost / bounds
+//   chunk NS [48,64)  N_s[9] Sigma_s^{-1}[6] -                  block LDL' factor
+// SHARED MEMORY (per warp): cold per-stage fields (termination checks, outputs), one column per lane,
+// field f of stage (lane, j) at S[(f*C + j)*32 + lane]; then the scratch / scan region, read ACROSS lanes:
+// the raw path slice (TMA destination), the serial factorisation's work arrays, and the lane-level prefix
+// products of the two scans.
 // ------------------------------------------------------------------------------------------------
 enum : int {
+    T_STRIDE = 64,
+    T_F = 0, T_G = 16, T_H = 32, T_NS = 48,
+    // offsets inside the chunks
+    FC_RHO = 0, FC_RINV = 5, FC_IV = 10, FC_IK = 11, FC_RB31 = 12, FC_RB22 = 13,
+    GC_S = 0, GC_M = 5, GC_B22 = 8, GC_B31 = 9, GC_A = 10,   // a11 a12 a21 a22 a31 a33
+    HC_Q = 0, HC_BE = 2, HC_LB = 5, HC_UB = 10,
+    NC_N = 0, NC_SI = 9
+};
+enum : int {
     F_XS = 0, F_YS, F_PSI, F_VEL,   // ReferencePath rows needed after the solves (paths.py:4-72)
-    K_M,                            // 3: coefficient of x_s in its own equality block (raw -1)
-    K_A = K_M + 3,                  // 6: a11 a12 a21 a22 a31 a33 of A_s (rows of block s+1)
-    K_B = K_A + 6,                  // 2: b22 b31 of B_{s-1} (rows of block s)
-    K_S = K_B + 2,                  // 5: bound ("identity") rows
-    K_Q = K_S + 5,                  // 2: q of (v, kappa_cmd); the state part of q is exactly zero
-    K_IV = K_Q + 2, K_IK,           // 1/K_uu of the two inputs
-    K_RB31, K_RB22,                 // rho_eq * b31, rho_eq * b22
-    K_BE,                           // 3: scaled equality right-hand side (l == u)
-    K_LB = K_BE + 3,                // 5
-    K_UB = K_LB + 5,                // 5
-    K_RHO = K_UB + 5,               // 5: rho of the bound rows (by class; rewritten with every rho update)
-    K_RINV = K_RHO + 5,             // 5: 1/rho of the bound rows
-    K_P = K_RINV + 5,               // 5: diagonal of P            (termination checks only)
-    K_DI = K_P + 5,                 // 5: 1/D                      (termination checks, outputs)
-    K_EEI = K_DI + 5,               // 3: 1/E of the equality block (termination checks only)
-    K_EBI = K_EEI + 3,              // 5: 1/E of the bound rows     (termination checks only)
-    K_N = K_EBI + 5,                // 9: N_s = -S_{s,s-1} Sigma_{s-1}^{-1}   (row major)
-    K_SI = K_N + 9,                 // 6: Sigma_s^{-1}  (00 10 11 20 21 22)
-    K_FIELDS = K_SI + 6
+    K_P,                            // 5: diagonal of P
+    K_DI = K_P + 5,                 // 5: 1/D
+    K_EEI = K_DI + 5,               // 3: 1/E of the equality block
+    K_EBI = K_EEI + 3,              // 5: 1/E of the bound rows
+    K_FIELDS = K_EBI + 5,
+    // work arrays of the factorisations inside the scratch region (per-stage columns like the fields above)
+    W_SS = 0,                       // 6: S_ss -> Sigma_s^{-1}
+    W_OFF = 6,                      // 9: S_{s,s-1} -> N_s
+    W_FIELDS = 15
 };
 
 template <int C>
 struct Layout {
-    static constexpr int kDoubles = (K_FIELDS * C + kLevels * 9) * 32;
+    static constexpr int kScratch = ((W_FIELDS * C > kLevels * 9) ? W_FIELDS * C : kLevels * 9) * 32;
+    static constexpr int kDoubles = K_FIELDS * C * 32 + kScratch;   // shared memory per warp
+    static constexpr int kTmemDoubles = T_STRIDE * C;               // tensor memory per lane
+    static constexpr int kTmemCols = (2 * kTmemDoubles <= 128) ? 128 : ((2 * kTmemDoubles <= 256) ? 256 : 512);
 };
 template <int C>
 constexpr int smem_doubles()
@@ -207,15 +221,21 @@ AC_DEV VD support(const VD& dy, const VD& lo, const VD& hi)
 // ------------------------------------------------------------------------------------------------
 template <int C>
 struct Ctx {
-    double* S;   // base of this instance's shared-memory block
+    double* S;   // base of this instance's (warp's) shared-memory block
+    Tm tm;       // base of this instance's tensor-memory block (the warp's lane quarter)
     int H, n;
     const acmpc_config* cfg;
     VI lane;
     AC_MEM double* col(int f, int j) const { return S + (f * C + j) * 32; }
     AC_MEM VD ld(int f, int j) const { return ld_lane(col(f, j)); }
     AC_MEM void st(int f, int j, const VD& v) const { st_lane(col(f, j), v); }
-    AC_MEM double* scan(int lvl, int e) const { return S + (K_FIELDS * C + lvl * 9 + e) * 32; }
+    AC_MEM double* scratch() const { return S + K_FIELDS * C * 32; }
+    AC_MEM double* wcol(int f, int j) const { return scratch() + (f * C + j) * 32; }
+    AC_MEM double* scan(int lvl, int e) const { return scratch() + (lvl * 9 + e) * 32; }
     AC_MEM VI stage(int j) const { return lane * C + j; }
+    // tensor-memory chunk `ch` (T_F, T_G, T_H, T_NS) of own stage j
+    AC_MEM void tld(int ch, int j, VD (&o)[16]) const { tm_ld<16>(tm, j * T_STRIDE + ch, o); }
+    AC_MEM void tst(int ch, int j, const VD (&v)[16]) const { tm_st<16>(tm, j * T_STRIDE + ch, v); }
 };
 
 // value held by the NEXT stage (s+1) for every own stage; 0 beyond lane 31
@@ -301,18 +321,24 @@ AC_DEV void pull_prev_rot(const VD (&v)[C][K], VD (&o)[C][K])
     }
 }
 
-// o += M v  /  o += M' v   (M row major 3x3)
-AC_DEV void mv_acc(const VD (&M)[9], const VD (&v)[3], VD (&o)[3])
+// o += M v  /  o += M' v   (M row major 3x3, 9 consecutive values), written as FMA chains
+AC_DEV void mv_acc9(const VD* M, const VD (&v)[3], VD (&o)[3])
 {
-    o[0] = o[0] + (M[0] * v[0] + M[1] * v[1] + M[2] * v[2]);
-    o[1] = o[1] + (M[3] * v[0] + M[4] * v[1] + M[5] * v[2]);
-    o[2] = o[2] + (M[6] * v[0] + M[7] * v[1] + M[8] * v[2]);
+    AC_UNROLL
+    for (int r = 0; r < 3; ++r) {
+        o[r] = M[3 * r] * v[0] + o[r];
+        o[r] = M[3 * r + 1] * v[1] + o[r];
+        o[r] = M[3 * r + 2] * v[2] + o[r];
+    }
 }
-AC_DEV void mtv_acc(const VD (&M)[9], const VD (&v)[3], VD (&o)[3])
+AC_DEV void mtv_acc9(const VD* M, const VD (&v)[3], VD (&o)[3])
 {
-    o[0] = o[0] + (M[0] * v[0] + M[3] * v[1] + M[6] * v[2]);
-    o[1] = o[1] + (M[1] * v[0] + M[4] * v[1] + M[7] * v[2]);
-    o[2] = o[2] + (M[2] * v[0] + M[5] * v[1] + M[8] * v[2]);
+    AC_UNROLL
+    for (int r = 0; r < 3; ++r) {
+        o[r] = M[r] * v[0] + o[r];
+        o[r] = M[3 + r] * v[1] + o[r];
+        o[r] = M[6 + r] * v[2] + o[r];
+    }
 }
 
 // ReferencePath rows of the lane's stages, in registers while the QPs are assembled
@@ -451,7 +477,7 @@ struct SpeedQP {
     }
 
     // reduced matrix K = P + sigma + A' rho A (tridiagonal) -> LDL' -> scan coefficients.
-    // scratch: two per-stage columns of shared memory (K_N+0, K_N+1: dead until the control QP)
+    // scratch: two per-stage work columns of shared memory
     AC_MEM void factor()
     {
         const double sigma = c.cfg->sigma;
@@ -466,8 +492,8 @@ struct SpeedQP {
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
             VD d = p[j] + VD(sigma) + rho_b[j] * ss[j] * ss[j] + rho_a[j] * al[j] * al[j] + tp[j];
-            c.st(K_N + 0, j, d);
-            c.st(K_N + 1, j, rho_a[j] * al[j] * au[j]);   // (i, i+1) entry, 0 without a row
+            st_lane(c.wcol(0, j), d);
+            st_lane(c.wcol(1, j), rho_a[j] * al[j] * au[j]);   // (i, i+1) entry, 0 without a row
         }
         warp_sync();
         // serial LDL' (every lane runs it on broadcast reads; lane 0 publishes)
@@ -476,8 +502,8 @@ struct SpeedQP {
             int s = 0;
             for (int l = 0; l < 32 && s < n; ++l)
                 for (int j = 0; j < C && s < n; ++j, ++s) {
-                    double* pd = c.col(K_N + 0, j) + l;
-                    double* po = c.col(K_N + 1, j) + l;
+                    double* pd = c.wcol(0, j) + l;
+                    double* po = c.wcol(1, j) + l;
                     double dd = *pd, oo = *po;
                     double lw = oprev * dprev;          // L_{s,s-1}
                     double piv = dd - lw * oprev;
@@ -494,8 +520,8 @@ struct SpeedQP {
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
             VB ok = vi_lt(c.stage(j), n);
-            dinv[j] = vsel(ok, c.ld(K_N + 0, j), VD(0.0));
-            nl[j] = vsel(ok, c.ld(K_N + 1, j), VD(0.0));
+            dinv[j] = vsel(ok, ld_lane(c.wcol(0, j)), VD(0.0));
+            nl[j] = vsel(ok, ld_lane(c.wcol(1, j)), VD(0.0));
         }
         warp_sync();
         VD f = nl[0];
@@ -742,7 +768,7 @@ struct ControlQP {
     AC_MEM explicit ControlQP(const Ctx<C>& ctx) : c(ctx), n(ctx.n), H(ctx.H) {}
 
     // linearise + stack (dynamics.py:65-103, solvers/control.py:26-79), OSQP scale_data (Ruiz) and
-    // set_rho_vec classes; the scaled problem goes to shared memory.
+    // set_rho_vec classes; the scaled problem goes to tensor memory (chunks G, H) and shared memory (cold).
     AC_MEM void setup(const PathRegs<C>& path, const VD (&vel)[C], double offset)
     {
         const acmpc_config& g = *c.cfg;
@@ -865,7 +891,7 @@ struct ControlQP {
         for (int j = 0; j < C; ++j) {
             VI st = c.stage(j);
             VB isx = vi_lt(st, H), hasU = vi_ge(st, 1) & isx, first = vi_eq(st, 0);
-            VD lo[5], hi[5], be[3];
+            VD lo[5], hi[5], be[3], G[16], Hc[16];
             lo[0] = vsel(first, VD(x0[0]), (-wp[j] / VD(2.0)) + VD(margin));
             hi[0] = vsel(first, VD(x0[0]), (wp[j] / VD(2.0)) - VD(margin));
             lo[1] = VD(-kInfty), hi[1] = VD(kInfty);
@@ -881,10 +907,10 @@ struct ControlQP {
                 VB real = (e < 3) ? isx : hasU;
                 VD l = vsel(real, lo[e] * EB[j][e], VD(0.0)), u = vsel(real, hi[e] * EB[j][e], VD(0.0));
                 bits = bits | (row_class(l, u) << (2 * e));
-                c.st(K_LB + e, j, l), c.st(K_UB + e, j, u);
-                c.st(K_S + e, j, s[j][e]), c.st(K_P + e, j, P[j][e]);
+                Hc[HC_LB + e] = l, Hc[HC_UB + e] = u;
+                G[GC_S + e] = s[j][e];
                 VD dinv = VD(1.0) / D[j][e];
-                c.st(K_DI + e, j, dinv), c.st(K_EBI + e, j, VD(1.0) / EB[j][e]);
+                c.st(K_P + e, j, P[j][e]), c.st(K_DI + e, j, dinv), c.st(K_EBI + e, j, VD(1.0) / EB[j][e]);
                 if (e >= 3) {
                     nqu = vmax(nqu, vabs(dinv * q[j][e - 3]));
                     nqs = vmax(nqs, vabs(q[j][e - 3]));
@@ -892,13 +918,14 @@ struct ControlQP {
             }
             cls[j] = bits;
             for (int r = 0; r < 3; ++r) {
-                c.st(K_BE + r, j, vsel(isx, be[r] * EE[j][r], VD(0.0)));
+                Hc[HC_BE + r] = vsel(isx, be[r] * EE[j][r], VD(0.0));
                 c.st(K_EEI + r, j, VD(1.0) / EE[j][r]);
-                c.st(K_M + r, j, m[j][r]);
+                G[GC_M + r] = m[j][r];
             }
-            for (int e = 0; e < 6; ++e) c.st(K_A + e, j, a[j][e]);
-            c.st(K_B + 0, j, b[j][0]), c.st(K_B + 1, j, b[j][1]);
-            c.st(K_Q + 0, j, q[j][0]), c.st(K_Q + 1, j, q[j][1]);
+            for (int e = 0; e < 6; ++e) G[GC_A + e] = a[j][e];
+            G[GC_B22] = b[j][0], G[GC_B31] = b[j][1];
+            Hc[HC_Q + 0] = q[j][0], Hc[HC_Q + 1] = q[j][1], Hc[15] = VD(0.0);
+            c.tst(T_G, j, G), c.tst(T_H, j, Hc);
         }
         nq_unscaled = wmax(nqu);
         nq_scaled = wmax(nqs);
@@ -909,31 +936,36 @@ struct ControlQP {
     AC_MEM void factor()
     {
         const double sigma = c.cfg->sigma, re = R.rho_eq;
-        VD g2[C][2], g2n[C][2], av[C][6], ap[C][6];
+        VD g2[C][2], g2n[C][2], av[C][6], ap[C][6], mv[C][3], dg[C][3];
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            for (int e = 0; e < 5; ++e) c.st(K_RHO + e, j, R.of(cls[j], 2 * e)), c.st(K_RINV + e, j, R.inv_of(cls[j], 2 * e));
-            VD b22 = c.ld(K_B + 0, j), b31 = c.ld(K_B + 1, j), s3 = c.ld(K_S + 3, j), s4 = c.ld(K_S + 4, j);
-            VD kv = c.ld(K_P + 3, j) + VD(sigma) + R.of(cls[j], 6) * s3 * s3 + VD(re) * b31 * b31;
-            VD kk = c.ld(K_P + 4, j) + VD(sigma) + R.of(cls[j], 8) * s4 * s4 + VD(re) * b22 * b22;
+            VD G[16], F[16];
+            c.tld(T_G, j, G);
+            const VD b22 = G[GC_B22], b31 = G[GC_B31], s3 = G[GC_S + 3], s4 = G[GC_S + 4];
+            for (int e = 0; e < 5; ++e) F[FC_RHO + e] = R.of(cls[j], 2 * e), F[FC_RINV + e] = R.inv_of(cls[j], 2 * e);
+            VD kv = c.ld(K_P + 3, j) + VD(sigma) + F[FC_RHO + 3] * s3 * s3 + VD(re) * b31 * b31;
+            VD kk = c.ld(K_P + 4, j) + VD(sigma) + F[FC_RHO + 4] * s4 * s4 + VD(re) * b22 * b22;
             VD iv = VD(1.0) / kv, ik = VD(1.0) / kk;
             VD rb31 = VD(re) * b31, rb22 = VD(re) * b22;
-            c.st(K_IV, j, iv), c.st(K_IK, j, ik), c.st(K_RB31, j, rb31), c.st(K_RB22, j, rb22);
+            F[FC_IV] = iv, F[FC_IK] = ik, F[FC_RB31] = rb31, F[FC_RB22] = rb22, F[14] = VD(0.0), F[15] = VD(0.0);
+            c.tst(T_F, j, F);
             g2[j][0] = iv * rb31 * rb31;   // gv
             g2[j][1] = ik * rb22 * rb22;   // gk
-            for (int e = 0; e < 6; ++e) av[j][e] = c.ld(K_A + e, j);
+            for (int e = 0; e < 6; ++e) av[j][e] = G[GC_A + e];
+            for (int r = 0; r < 3; ++r) {
+                mv[j][r] = G[GC_M + r];
+                const VD sr = G[GC_S + r];
+                dg[j][r] = c.ld(K_P + r, j) + VD(sigma) + F[FC_RHO + r] * sr * sr + VD(re) * mv[j][r] * mv[j][r];
+            }
         }
         pull_next_k<C, 2>(g2, g2n);
         pull_prev_k<C, 6>(av, ap);
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            VD m0 = c.ld(K_M + 0, j), m1 = c.ld(K_M + 1, j), m2 = c.ld(K_M + 2, j);
-            VD s0 = c.ld(K_S + 0, j), s1 = c.ld(K_S + 1, j), s2 = c.ld(K_S + 2, j);
+            const VD m0 = mv[j][0], m1 = mv[j][1], m2 = mv[j][2];
             const VD gv = g2[j][0], gk = g2[j][1], gvn = g2n[j][0], gkn = g2n[j][1];
             const VD a11 = av[j][0], a12 = av[j][1], a21 = av[j][2], a22 = av[j][3], a31 = av[j][4], a33 = av[j][5];
-            VD k00 = c.ld(K_P + 0, j) + VD(sigma) + R.of(cls[j], 0) * s0 * s0 + VD(re) * m0 * m0;
-            VD k11 = c.ld(K_P + 1, j) + VD(sigma) + R.of(cls[j], 2) * s1 * s1 + VD(re) * m1 * m1;
-            VD k22 = c.ld(K_P + 2, j) + VD(sigma) + R.of(cls[j], 4) * s2 * s2 + VD(re) * m2 * m2;
+            VD k00 = dg[j][0], k11 = dg[j][1], k22 = dg[j][2];
             // elimination of the own input u_{s-1}
             k11 = k11 - gk * m1 * m1;
             k22 = k22 - gv * m2 * m2;
@@ -943,19 +975,19 @@ struct ControlQP {
             k11 = k11 + VD(re) * (a12 * a12 + a22 * a22) - gkn * a22 * a22;
             VD k20 = VD(re) * (a31 * a33) - gvn * a31 * a33;
             k22 = k22 + VD(re) * (a33 * a33) - gvn * a33 * a33;
-            c.st(K_SI + 0, j, k00), c.st(K_SI + 1, j, k10), c.st(K_SI + 2, j, k11);
-            c.st(K_SI + 3, j, k20), c.st(K_SI + 4, j, VD(0.0)), c.st(K_SI + 5, j, k22);
+            st_lane(c.wcol(W_SS + 0, j), k00), st_lane(c.wcol(W_SS + 1, j), k10), st_lane(c.wcol(W_SS + 2, j), k11);
+            st_lane(c.wcol(W_SS + 3, j), k20), st_lane(c.wcol(W_SS + 4, j), VD(0.0)), st_lane(c.wcol(W_SS + 5, j), k22);
             // S_{s,s-1}: rows of x_s, columns of x_{s-1} (entries of A_{s-1})
             const VD p11 = ap[j][0], p12 = ap[j][1], p21 = ap[j][2], p22 = ap[j][3], p31 = ap[j][4], p33 = ap[j][5];
-            c.st(K_N + 0, j, m0 * VD(re) * p11);
-            c.st(K_N + 1, j, m0 * VD(re) * p12);
-            c.st(K_N + 2, j, VD(0.0));
-            c.st(K_N + 3, j, m1 * (VD(re) * p21 - gk * p21));
-            c.st(K_N + 4, j, m1 * (VD(re) * p22 - gk * p22));
-            c.st(K_N + 5, j, VD(0.0));
-            c.st(K_N + 6, j, m2 * (VD(re) * p31 - gv * p31));
-            c.st(K_N + 7, j, VD(0.0));
-            c.st(K_N + 8, j, m2 * (VD(re) * p33 - gv * p33));
+            st_lane(c.wcol(W_OFF + 0, j), m0 * VD(re) * p11);
+            st_lane(c.wcol(W_OFF + 1, j), m0 * VD(re) * p12);
+            st_lane(c.wcol(W_OFF + 2, j), VD(0.0));
+            st_lane(c.wcol(W_OFF + 3, j), m1 * (VD(re) * p21 - gk * p21));
+            st_lane(c.wcol(W_OFF + 4, j), m1 * (VD(re) * p22 - gk * p22));
+            st_lane(c.wcol(W_OFF + 5, j), VD(0.0));
+            st_lane(c.wcol(W_OFF + 6, j), m2 * (VD(re) * p31 - gv * p31));
+            st_lane(c.wcol(W_OFF + 7, j), VD(0.0));
+            st_lane(c.wcol(W_OFF + 8, j), m2 * (VD(re) * p33 - gv * p33));
         }
         warp_sync();
         // serial block LDL': Sigma_s = S_ss - G_s S_{s,s-1}', G_s = S_{s,s-1} Sigma_{s-1}^{-1}; N_s = -G_s.
@@ -965,8 +997,8 @@ struct ControlQP {
             int s = 0;
             for (int l = 0; l < 32 && s < H; ++l)
                 for (int j = 0; j < C && s < H; ++j, ++s) {
-                    double* SI = c.col(K_SI, j) + l;
-                    double* NN = c.col(K_N, j) + l;
+                    double* SI = c.wcol(W_SS, j) + l;
+                    double* NN = c.wcol(W_OFF, j) + l;
                     const int st = C * 32;   // distance between consecutive fields
                     double a00 = SI[0 * st], a10 = SI[1 * st], a11 = SI[2 * st];
                     double a20 = SI[3 * st], a21 = SI[4 * st], a22 = SI[5 * st];
@@ -1007,18 +1039,27 @@ struct ControlQP {
                 }
         }
         warp_sync();
-        // lane-level prefix products for the scans: level L maps the carry of lane l - 2^L to lane l
+        // own stages' factor -> tensor memory; lane-level prefix products for the scans -> scratch region
+        // (level L maps the carry of lane l - 2^L to lane l)
         VD F[9];
-        for (int e = 0; e < 9; ++e) F[e] = c.ld(K_N + e, 0);
         AC_UNROLL
-        for (int j = 1; j < C; ++j) {
-            VD Nj[9], T[9];
-            for (int e = 0; e < 9; ++e) Nj[e] = c.ld(K_N + e, j);
-            for (int r = 0; r < 3; ++r)
-                for (int q = 0; q < 3; ++q)
-                    T[3 * r + q] = Nj[3 * r] * F[q] + Nj[3 * r + 1] * F[3 + q] + Nj[3 * r + 2] * F[6 + q];
-            for (int e = 0; e < 9; ++e) F[e] = T[e];
+        for (int j = 0; j < C; ++j) {
+            VD NS[16];
+            for (int e = 0; e < 9; ++e) NS[NC_N + e] = ld_lane(c.wcol(W_OFF + e, j));
+            for (int e = 0; e < 6; ++e) NS[NC_SI + e] = ld_lane(c.wcol(W_SS + e, j));
+            NS[15] = VD(0.0);
+            c.tst(T_NS, j, NS);
+            if (j == 0) {
+                for (int e = 0; e < 9; ++e) F[e] = NS[NC_N + e];
+            } else {
+                VD T[9];
+                for (int r = 0; r < 3; ++r)
+                    for (int q = 0; q < 3; ++q)
+                        T[3 * r + q] = NS[3 * r] * F[q] + NS[3 * r + 1] * F[3 + q] + NS[3 * r + 2] * F[6 + q];
+                for (int e = 0; e < 9; ++e) F[e] = T[e];
+            }
         }
+        warp_sync();   // every lane has read its work columns: the region now takes the scan matrices
         for (int L = 0; L < kLevels; ++L) {
             VD U[9], T[9];
             for (int e = 0; e < 9; ++e) {
@@ -1036,14 +1077,15 @@ struct ControlQP {
     // x~ = Schur^{-1} r for the state part: two affine scans over the stages (see file header)
     AC_MEM void block_solve(const VD (&r)[C][3], VD (&xt)[C][3])
     {
-        VD y[C][3], w[C][3], M[9];
+        VD y[C][3], w[C][3], M[9], NS[C][16];
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) c.tld(T_NS, j, NS[j]);
         // forward: local pass with zero carry-in, scan over lanes, local fix-up
         VD Y[3] = {r[0][0], r[0][1], r[0][2]};
         AC_UNROLL
         for (int j = 1; j < C; ++j) {
-            for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, j);
             VD T[3] = {r[j][0], r[j][1], r[j][2]};
-            mv_acc(M, Y, T);
+            mv_acc9(&NS[j][NC_N], Y, T);
             Y[0] = T[0], Y[1] = T[1], Y[2] = T[2];
         }
         // (the level matrices are zero on lanes < 2^L and N_0 is zero on lane 0: raw shuffles suffice)
@@ -1054,29 +1096,27 @@ struct ControlQP {
                 VD U[3];
                 for (int e = 0; e < 3; ++e) U[e] = shfl_up_raw(Y[e], 1 << L);
                 for (int e = 0; e < 9; ++e) M[e] = ld_lane(sp + e * 32);
-                mv_acc(M, U, Y);
+                mv_acc9(M, U, Y);
             }
         }
         {
             VD U[3];
             for (int e = 0; e < 3; ++e) U[e] = shfl_up_raw(Y[e], 1);
-            for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, 0);
             for (int e = 0; e < 3; ++e) y[0][e] = r[0][e];
-            mv_acc(M, U, y[0]);
+            mv_acc9(&NS[0][NC_N], U, y[0]);
         }
         AC_UNROLL
         for (int j = 1; j + 1 < C; ++j) {
-            for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, j);
             for (int e = 0; e < 3; ++e) y[j][e] = r[j][e];
-            mv_acc(M, y[j - 1], y[j]);
+            mv_acc9(&NS[j][NC_N], y[j - 1], y[j]);
         }
         if (C > 1)
             for (int e = 0; e < 3; ++e) y[C - 1][e] = Y[e];
         // diagonal
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            VD i00 = c.ld(K_SI + 0, j), i10 = c.ld(K_SI + 1, j), i11 = c.ld(K_SI + 2, j);
-            VD i20 = c.ld(K_SI + 3, j), i21 = c.ld(K_SI + 4, j), i22 = c.ld(K_SI + 5, j);
+            const VD i00 = NS[j][NC_SI + 0], i10 = NS[j][NC_SI + 1], i11 = NS[j][NC_SI + 2];
+            const VD i20 = NS[j][NC_SI + 3], i21 = NS[j][NC_SI + 4], i22 = NS[j][NC_SI + 5];
             w[j][0] = i00 * y[j][0] + i10 * y[j][1] + i20 * y[j][2];
             w[j][1] = i10 * y[j][0] + i11 * y[j][1] + i21 * y[j][2];
             w[j][2] = i20 * y[j][0] + i21 * y[j][1] + i22 * y[j][2];
@@ -1087,19 +1127,15 @@ struct ControlQP {
             for (int e = 0; e < 3; ++e) A[e] = w[C - 2][e];
             AC_UNROLL
             for (int j = C - 3; j >= 0; --j) {
-                for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, j + 1);
                 VD T[3] = {w[j][0], w[j][1], w[j][2]};
-                mtv_acc(M, A, T);
+                mtv_acc9(&NS[j + 1][NC_N], A, T);
                 A[0] = T[0], A[1] = T[1], A[2] = T[2];
             }
         }
         VD Z[3];
         {
             VD Hh[3] = {VD(0.0), VD(0.0), VD(0.0)};
-            if (C > 1) {
-                for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, 0);
-                mtv_acc(M, A, Hh);
-            }
+            if (C > 1) mtv_acc9(&NS[0][NC_N], A, Hh);
             for (int e = 0; e < 3; ++e) Z[e] = w[C - 1][e] + shfl_down0(Hh[e], 1);
         }
         {
@@ -1109,15 +1145,14 @@ struct ControlQP {
                 VD U[3];
                 for (int e = 0; e < 3; ++e) U[e] = shfl_down0(Z[e], 1 << L);
                 for (int e = 0; e < 9; ++e) M[e] = ld_lane_at(sp + e * 32, 1 << L);
-                mtv_acc(M, U, Z);
+                mtv_acc9(M, U, Z);
             }
         }
         for (int e = 0; e < 3; ++e) xt[C - 1][e] = Z[e];
         AC_UNROLL
         for (int j = C - 2; j >= 0; --j) {
-            for (int e = 0; e < 9; ++e) M[e] = c.ld(K_N + e, j + 1);
             for (int e = 0; e < 3; ++e) xt[j][e] = w[j][e];
-            mtv_acc(M, xt[j + 1], xt[j]);
+            mtv_acc9(&NS[j + 1][NC_N], xt[j + 1], xt[j]);
         }
     }
 
@@ -1125,67 +1160,69 @@ struct ControlQP {
     AC_MEM void iterate(bool keep_delta)
     {
         const double sigma = c.cfg->sigma, alpha = c.cfg->alpha, re = R.rho_eq;
-        VD t[C][3], tn[C][3], ru[C][2], r[C][3], xt[C][3];
+        VD t[C][3], tn[C][3], ru[C][2], r[C][3], xt[C][3], Aj[C][6];
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
+            VD F[16], G[16], Q[2];
+            c.tld(T_F, j, F), c.tld(T_G, j, G);
+            tm_ld<2>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
             VD w0 = VD(re) * ze[j][0] - ye[j][0], w1 = VD(re) * ze[j][1] - ye[j][1], w2 = VD(re) * ze[j][2] - ye[j][2];
-            VD wb3 = c.ld(K_RHO + 3, j) * zb[j][3] - yb[j][3], wb4 = c.ld(K_RHO + 4, j) * zb[j][4] - yb[j][4];
-            VD b22 = c.ld(K_B + 0, j), b31 = c.ld(K_B + 1, j);
-            ru[j][0] = VD(sigma) * x[j][3] + c.ld(K_S + 3, j) * wb3 + b31 * w2 - c.ld(K_Q + 0, j);
-            ru[j][1] = VD(sigma) * x[j][4] + c.ld(K_S + 4, j) * wb4 + b22 * w1 - c.ld(K_Q + 1, j);
-            VD pv = c.ld(K_IV, j) * ru[j][0], pk = c.ld(K_IK, j) * ru[j][1];
+            VD wb3 = F[FC_RHO + 3] * zb[j][3] - yb[j][3], wb4 = F[FC_RHO + 4] * zb[j][4] - yb[j][4];
+            ru[j][0] = VD(sigma) * x[j][3] + G[GC_S + 3] * wb3 + G[GC_B31] * w2 - Q[0];
+            ru[j][1] = VD(sigma) * x[j][4] + G[GC_S + 4] * wb4 + G[GC_B22] * w1 - Q[1];
+            VD pv = F[FC_IV] * ru[j][0], pk = F[FC_IK] * ru[j][1];
             t[j][0] = w0;
-            t[j][1] = w1 - c.ld(K_RB22, j) * pk;
-            t[j][2] = w2 - c.ld(K_RB31, j) * pv;
+            t[j][1] = w1 - F[FC_RB22] * pk;
+            t[j][2] = w2 - F[FC_RB31] * pv;
+            // the part of the state rhs that does not need the next stage
+            for (int q = 0; q < 3; ++q) {
+                VD wb = F[FC_RHO + q] * zb[j][q] - yb[j][q];
+                r[j][q] = VD(sigma) * x[j][q] + G[GC_S + q] * wb + G[GC_M + q] * t[j][q];
+            }
+            for (int e = 0; e < 6; ++e) Aj[j][e] = G[GC_A + e];
         }
         pull_next_raw<C, 3>(t, tn);
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            VD wb0 = c.ld(K_RHO + 0, j) * zb[j][0] - yb[j][0], wb1 = c.ld(K_RHO + 1, j) * zb[j][1] - yb[j][1],
-               wb2 = c.ld(K_RHO + 2, j) * zb[j][2] - yb[j][2];
-            r[j][0] = VD(sigma) * x[j][0] + c.ld(K_S + 0, j) * wb0 + c.ld(K_M + 0, j) * t[j][0] +
-                      (c.ld(K_A + 0, j) * tn[j][0] + c.ld(K_A + 2, j) * tn[j][1] + c.ld(K_A + 4, j) * tn[j][2]);
-            r[j][1] = VD(sigma) * x[j][1] + c.ld(K_S + 1, j) * wb1 + c.ld(K_M + 1, j) * t[j][1] +
-                      (c.ld(K_A + 1, j) * tn[j][0] + c.ld(K_A + 3, j) * tn[j][1]);
-            r[j][2] = VD(sigma) * x[j][2] + c.ld(K_S + 2, j) * wb2 + c.ld(K_M + 2, j) * t[j][2] +
-                      c.ld(K_A + 5, j) * tn[j][2];
+            r[j][0] = r[j][0] + (Aj[j][0] * tn[j][0] + Aj[j][2] * tn[j][1] + Aj[j][4] * tn[j][2]);
+            r[j][1] = r[j][1] + (Aj[j][1] * tn[j][0] + Aj[j][3] * tn[j][1]);
+            r[j][2] = r[j][2] + Aj[j][5] * tn[j][2];
         }
         block_solve(r, xt);
         // p^ = A_s x~_s goes up to stage s+1
         VD ph[C][3], cp[C][3];
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            ph[j][0] = c.ld(K_A + 0, j) * xt[j][0] + c.ld(K_A + 1, j) * xt[j][1];
-            ph[j][1] = c.ld(K_A + 2, j) * xt[j][0] + c.ld(K_A + 3, j) * xt[j][1];
-            ph[j][2] = c.ld(K_A + 4, j) * xt[j][0] + c.ld(K_A + 5, j) * xt[j][2];
+            ph[j][0] = Aj[j][0] * xt[j][0] + Aj[j][1] * xt[j][1];
+            ph[j][1] = Aj[j][2] * xt[j][0] + Aj[j][3] * xt[j][1];
+            ph[j][2] = Aj[j][4] * xt[j][0] + Aj[j][5] * xt[j][2];
         }
         pull_prev_rot<C, 3>(ph, cp);
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            VD e0 = c.ld(K_M + 0, j) * xt[j][0] + cp[j][0];
-            VD e1 = c.ld(K_M + 1, j) * xt[j][1] + cp[j][1];
-            VD e2 = c.ld(K_M + 2, j) * xt[j][2] + cp[j][2];
-            VD b22 = c.ld(K_B + 0, j), b31 = c.ld(K_B + 1, j);
-            VD utv = c.ld(K_IV, j) * (ru[j][0] - c.ld(K_RB31, j) * e2);
-            VD utk = c.ld(K_IK, j) * (ru[j][1] - c.ld(K_RB22, j) * e1);
-            VD zte[3] = {e0, e1 + b22 * utk, e2 + b31 * utv};
+            VD F[16], G[16], Hc[16];
+            c.tld(T_F, j, F), c.tld(T_G, j, G), c.tld(T_H, j, Hc);
+            VD e0 = G[GC_M + 0] * xt[j][0] + cp[j][0];
+            VD e1 = G[GC_M + 1] * xt[j][1] + cp[j][1];
+            VD e2 = G[GC_M + 2] * xt[j][2] + cp[j][2];
+            VD utv = F[FC_IV] * (ru[j][0] - F[FC_RB31] * e2);
+            VD utk = F[FC_IK] * (ru[j][1] - F[FC_RB22] * e1);
+            VD zte[3] = {e0, e1 + G[GC_B22] * utk, e2 + G[GC_B31] * utv};
             VD xv[5] = {xt[j][0], xt[j][1], xt[j][2], utv, utk};
             // equality rows: l == u == b
             for (int q = 0; q < 3; ++q) {
-                VD b = c.ld(K_BE + q, j);
                 VD zh = VD(alpha) * zte[q] + VD(1.0 - alpha) * ze[j][q];
-                VD zn = b;   // projection onto [b, b]
+                VD zn = Hc[HC_BE + q];   // projection onto [b, b]
                 VD dy = VD(re) * (zh - zn);
                 ze[j][q] = zn;
                 ye[j][q] = ye[j][q] + dy;
                 dye[j][q] = dy;
             }
             for (int e = 0; e < 5; ++e) {
-                VD rho = c.ld(K_RHO + e, j), rinv = c.ld(K_RINV + e, j);
-                VD zt = c.ld(K_S + e, j) * xv[e];
+                VD zt = G[GC_S + e] * xv[e];
                 VD zh = VD(alpha) * zt + VD(1.0 - alpha) * zb[j][e];
-                VD zn = vclamp(zh + rinv * yb[j][e], c.ld(K_LB + e, j), c.ld(K_UB + e, j));
-                VD dy = rho * (zh - zn);
+                VD zn = vclamp(zh + F[FC_RINV + e] * yb[j][e], Hc[HC_LB + e], Hc[HC_UB + e]);
+                VD dy = F[FC_RHO + e] * (zh - zn);
                 zb[j][e] = zn;
                 yb[j][e] = yb[j][e] + dy;
                 dyb[j][e] = dy;
@@ -1199,19 +1236,20 @@ struct ControlQP {
     // A v on the equality rows owned by each stage (v: 5 local variables per stage)
     AC_MEM void eq_rows(const VD (&v)[C][5], VD (&o)[C][3])
     {
-        VD ph[C][3], cp[C][3];
+        VD ph[C][3], cp[C][3], G[C][16];
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            ph[j][0] = c.ld(K_A + 0, j) * v[j][0] + c.ld(K_A + 1, j) * v[j][1];
-            ph[j][1] = c.ld(K_A + 2, j) * v[j][0] + c.ld(K_A + 3, j) * v[j][1];
-            ph[j][2] = c.ld(K_A + 4, j) * v[j][0] + c.ld(K_A + 5, j) * v[j][2];
+            c.tld(T_G, j, G[j]);
+            ph[j][0] = G[j][GC_A + 0] * v[j][0] + G[j][GC_A + 1] * v[j][1];
+            ph[j][1] = G[j][GC_A + 2] * v[j][0] + G[j][GC_A + 3] * v[j][1];
+            ph[j][2] = G[j][GC_A + 4] * v[j][0] + G[j][GC_A + 5] * v[j][2];
         }
         pull_prev_k<C, 3>(ph, cp);
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            o[j][0] = c.ld(K_M + 0, j) * v[j][0] + cp[j][0];
-            o[j][1] = c.ld(K_M + 1, j) * v[j][1] + cp[j][1] + c.ld(K_B + 0, j) * v[j][4];
-            o[j][2] = c.ld(K_M + 2, j) * v[j][2] + cp[j][2] + c.ld(K_B + 1, j) * v[j][3];
+            o[j][0] = G[j][GC_M + 0] * v[j][0] + cp[j][0];
+            o[j][1] = G[j][GC_M + 1] * v[j][1] + cp[j][1] + G[j][GC_B22] * v[j][4];
+            o[j][2] = G[j][GC_M + 2] * v[j][2] + cp[j][2] + G[j][GC_B31] * v[j][3];
         }
     }
     // A' (ve, vb) on the columns owned by each stage
@@ -1221,13 +1259,14 @@ struct ControlQP {
         pull_next_k<C, 3>(ve, vn);
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            o[j][0] = c.ld(K_S + 0, j) * vb[j][0] + c.ld(K_M + 0, j) * ve[j][0] +
-                      (c.ld(K_A + 0, j) * vn[j][0] + c.ld(K_A + 2, j) * vn[j][1] + c.ld(K_A + 4, j) * vn[j][2]);
-            o[j][1] = c.ld(K_S + 1, j) * vb[j][1] + c.ld(K_M + 1, j) * ve[j][1] +
-                      (c.ld(K_A + 1, j) * vn[j][0] + c.ld(K_A + 3, j) * vn[j][1]);
-            o[j][2] = c.ld(K_S + 2, j) * vb[j][2] + c.ld(K_M + 2, j) * ve[j][2] + c.ld(K_A + 5, j) * vn[j][2];
-            o[j][3] = c.ld(K_S + 3, j) * vb[j][3] + c.ld(K_B + 1, j) * ve[j][2];
-            o[j][4] = c.ld(K_S + 4, j) * vb[j][4] + c.ld(K_B + 0, j) * ve[j][1];
+            VD G[16];
+            c.tld(T_G, j, G);
+            o[j][0] = G[GC_S + 0] * vb[j][0] + G[GC_M + 0] * ve[j][0] +
+                      (G[GC_A + 0] * vn[j][0] + G[GC_A + 2] * vn[j][1] + G[GC_A + 4] * vn[j][2]);
+            o[j][1] = G[GC_S + 1] * vb[j][1] + G[GC_M + 1] * ve[j][1] + (G[GC_A + 1] * vn[j][0] + G[GC_A + 3] * vn[j][1]);
+            o[j][2] = G[GC_S + 2] * vb[j][2] + G[GC_M + 2] * ve[j][2] + G[GC_A + 5] * vn[j][2];
+            o[j][3] = G[GC_S + 3] * vb[j][3] + G[GC_B31] * ve[j][2];
+            o[j][4] = G[GC_S + 4] * vb[j][4] + G[GC_B22] * ve[j][1];
         }
     }
 
@@ -1240,10 +1279,13 @@ struct ControlQP {
         at_cols(ye, yb, aty);
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
+            VD S5[8], Q[2];
+            tm_ld<8>(c.tm, j * T_STRIDE + T_G + GC_S, S5);
+            tm_ld<2>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
             for (int r = 0; r < 3; ++r) acc_row(v, ax[j][r], ze[j][r], c.ld(K_EEI + r, j));
             for (int e = 0; e < 5; ++e) {
-                acc_row(v, c.ld(K_S + e, j) * x[j][e], zb[j][e], c.ld(K_EBI + e, j));
-                VD q = (e >= 3) ? c.ld(K_Q + e - 3, j) : VD(0.0);
+                acc_row(v, S5[e] * x[j][e], zb[j][e], c.ld(K_EBI + e, j));
+                VD q = (e >= 3) ? Q[e - 3] : VD(0.0);
                 acc_col(v, q, c.ld(K_P + e, j) * x[j][e], aty[j][e], c.ld(K_DI + e, j));
             }
         }
@@ -1255,13 +1297,15 @@ struct ControlQP {
         VD nrm = VD(0.0), lhs = VD(0.0);
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
+            VD Hc[16];
+            c.tld(T_H, j, Hc);
             for (int r = 0; r < 3; ++r) {   // equality rows: finite bounds, no projection
-                VD b = c.ld(K_BE + r, j);
+                VD b = Hc[HC_BE + r];
                 nrm = vmax(nrm, vabs(dye[j][r] / c.ld(K_EEI + r, j)));
                 lhs = lhs + support(dye[j][r], b, b);
             }
             for (int e = 0; e < 5; ++e) {
-                VD lo = c.ld(K_LB + e, j), hi = c.ld(K_UB + e, j);
+                VD lo = Hc[HC_LB + e], hi = Hc[HC_UB + e];
                 dyb[j][e] = project_dy(dyb[j][e], lo, hi);
                 nrm = vmax(nrm, vabs(dyb[j][e] / c.ld(K_EBI + e, j)));
                 lhs = lhs + support(dyb[j][e], lo, hi);
@@ -1281,13 +1325,16 @@ struct ControlQP {
     {
         VD nrm = VD(0.0), qdx = VD(0.0), pm = VD(0.0);
         AC_UNROLL
-        for (int j = 0; j < C; ++j)
+        for (int j = 0; j < C; ++j) {
+            VD Q[2];
+            tm_ld<2>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
             for (int e = 0; e < 5; ++e) {
                 VD di = c.ld(K_DI + e, j);
                 nrm = vmax(nrm, vabs(dx[j][e] / di));
-                if (e >= 3) qdx = qdx + c.ld(K_Q + e - 3, j) * dx[j][e];
+                if (e >= 3) qdx = qdx + Q[e - 3] * dx[j][e];
                 pm = vmax(pm, vabs(di * (c.ld(K_P + e, j) * dx[j][e])));
             }
+        }
         double nr = wmax(nrm), qd = wsum(qdx), pmx = wmax(pm);
         if (uni(!(nr > eps) || !(qd < -cs * eps * nr) || !(pmx < cs * eps * nr))) return 0;
         VD adx[C][3];
@@ -1296,13 +1343,16 @@ struct ControlQP {
         const VD lim = VD(eps * nr);
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
+            VD Hc[16], S5[8];
+            c.tld(T_H, j, Hc);
+            tm_ld<8>(c.tm, j * T_STRIDE + T_G + GC_S, S5);
             for (int r = 0; r < 3; ++r) {   // equality rows: both bounds finite
                 VD a = adx[j][r] * c.ld(K_EEI + r, j);
                 bad = bad | (a > lim) | (a < -lim);
             }
             for (int e = 0; e < 5; ++e) {
-                VD a = c.ld(K_EBI + e, j) * (c.ld(K_S + e, j) * dx[j][e]);
-                VD lo = c.ld(K_LB + e, j), hi = c.ld(K_UB + e, j);
+                VD a = c.ld(K_EBI + e, j) * (S5[e] * dx[j][e]);
+                VD lo = Hc[HC_LB + e], hi = Hc[HC_UB + e];
                 bad = bad | ((hi < VD(kBig)) & (a > lim)) | ((lo > VD(-kBig)) & (a < -lim));
             }
         }
@@ -1379,7 +1429,7 @@ struct ControlQP {
             for (int e = 0; e < 5; ++e) {
                 VD xe = x[j][e];
                 obj = obj + VD(0.5) * c.ld(K_P + e, j) * xe * xe;
-                if (e >= 3) obj = obj + c.ld(K_Q + e - 3, j) * xe;
+                if (e >= 3) obj = obj + tm_ld1(c.tm, j * T_STRIDE + T_H + HC_Q + e - 3) * xe;
             }
         info.obj_val = final_obj(status, wsum(obj) * cinv);
     }

@@ -297,6 +297,27 @@ AC_DEV VD ld_lane_at(const double* base, int off)
     return r;
 }
 AC_DEV VB vb_not(const VB& a) { return !a; }
+
+// ---- tensor memory (TMEM) as a lane-private scratchpad: the emulation models it as [double column][lane]
+struct Tm {
+    double* p;
+};
+template <int N>
+AC_DEV void tm_ld(const Tm& t, int dcol, VD (&o)[N])
+{
+    for (int k = 0; k < N; ++k) AC_FOR_LANES o[k].v[i_] = t.p[(dcol + k) * 32 + i_];
+}
+template <int N>
+AC_DEV void tm_st(const Tm& t, int dcol, const VD (&v)[N])
+{
+    for (int k = 0; k < N; ++k) AC_FOR_LANES t.p[(dcol + k) * 32 + i_] = v[k].v[i_];
+}
+AC_DEV VD tm_ld1(const Tm& t, int dcol)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = t.p[dcol * 32 + i_];
+    return r;
+}
 AC_DEV void warp_sync() {}
 
 }  // namespace acmpc
@@ -382,6 +403,141 @@ AC_DEV VD ld_lane_at(const double* base, int off)
     return base[i < 32 ? i : 31];
 }
 AC_DEV VB vb_not(bool a) { return !a; }
+
+// ---- tensor memory (TMEM) as a lane-private scratchpad.  One double = two 32-bit columns of the lane's
+// row; `a` = TMEM address (lane quarter of the warp << 16 | first column of the instance).  Every load is
+// issued together with its tcgen05.wait::ld so the destination registers are defined when the asm ends.
+struct Tm {
+    uint32_t a;
+};
+AC_DEV void tm_ld_raw1(uint32_t addr, double* o)
+{
+    uint32_t r[2];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1])
+                 : "r"(addr)
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 1; ++k) o[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+}
+AC_DEV void tm_st_raw1(uint32_t addr, const double* v)
+{
+    uint32_t r[2];
+#pragma unroll
+    for (int k = 0; k < 1; ++k) r[2 * k] = (uint32_t)__double2loint(v[k]), r[2 * k + 1] = (uint32_t)__double2hiint(v[k]);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%2], {%0,%1};\n\ttcgen05.wait::st.sync.aligned;"
+                 :
+                 : "r"(r[0]), "r"(r[1]), "r"(addr)
+                 : "memory");
+}
+AC_DEV void tm_ld_raw2(uint32_t addr, double* o)
+{
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr)
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 2; ++k) o[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+}
+AC_DEV void tm_st_raw2(uint32_t addr, const double* v)
+{
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) r[2 * k] = (uint32_t)__double2loint(v[k]), r[2 * k + 1] = (uint32_t)__double2hiint(v[k]);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};\n\ttcgen05.wait::st.sync.aligned;"
+                 :
+                 : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(addr)
+                 : "memory");
+}
+AC_DEV void tm_ld_raw4(uint32_t addr, double* o)
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr)
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+}
+AC_DEV void tm_st_raw4(uint32_t addr, const double* v)
+{
+    uint32_t r[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[2 * k] = (uint32_t)__double2loint(v[k]), r[2 * k + 1] = (uint32_t)__double2hiint(v[k]);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};\n\ttcgen05.wait::st.sync.aligned;"
+                 :
+                 : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(addr)
+                 : "memory");
+}
+AC_DEV void tm_ld_raw8(uint32_t addr, double* o)
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(addr)
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+}
+AC_DEV void tm_st_raw8(uint32_t addr, const double* v)
+{
+    uint32_t r[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[2 * k] = (uint32_t)__double2loint(v[k]), r[2 * k + 1] = (uint32_t)__double2hiint(v[k]);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};\n\ttcgen05.wait::st.sync.aligned;"
+                 :
+                 : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(addr)
+                 : "memory");
+}
+AC_DEV void tm_ld_raw16(uint32_t addr, double* o)
+{
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(addr)
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+}
+AC_DEV void tm_st_raw16(uint32_t addr, const double* v)
+{
+    uint32_t r[32];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r[2 * k] = (uint32_t)__double2loint(v[k]), r[2 * k + 1] = (uint32_t)__double2hiint(v[k]);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31};\n\ttcgen05.wait::st.sync.aligned;"
+                 :
+                 : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(addr)
+                 : "memory");
+}
+template <int N>
+AC_DEV void tm_ld(const Tm& t, int dcol, double (&o)[N])
+{
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16, "power-of-two chunk");
+    const uint32_t addr = t.a + 2u * (uint32_t)dcol;
+    if (N == 1) tm_ld_raw1(addr, o);
+    if (N == 2) tm_ld_raw2(addr, o);
+    if (N == 4) tm_ld_raw4(addr, o);
+    if (N == 8) tm_ld_raw8(addr, o);
+    if (N == 16) tm_ld_raw16(addr, o);
+}
+template <int N>
+AC_DEV void tm_st(const Tm& t, int dcol, const double (&v)[N])
+{
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16, "power-of-two chunk");
+    const uint32_t addr = t.a + 2u * (uint32_t)dcol;
+    if (N == 1) tm_st_raw1(addr, v);
+    if (N == 2) tm_st_raw2(addr, v);
+    if (N == 4) tm_st_raw4(addr, v);
+    if (N == 8) tm_st_raw8(addr, v);
+    if (N == 16) tm_st_raw16(addr, v);
+}
+AC_DEV double tm_ld1(const Tm& t, int dcol)
+{
+    double o[1];
+    tm_ld_raw1(t.a + 2u * (uint32_t)dcol, o);
+    return o[0];
+}
 AC_DEV void warp_sync() { __syncwarp(); }
 
 }  // namespace acmpc

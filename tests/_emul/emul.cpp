@@ -18,12 +18,15 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
 {
     const int H = cfg->horizon, n = H - 1;
     const size_t nd = (size_t)acmpc::smem_doubles<C>();
+    const size_t nt = (size_t)acmpc::Layout<C>::kTmemDoubles * 32;   // tensor-memory model: [double column][lane]
     double* smem = (double*)malloc(sizeof(double) * nd);
+    double* tmem = (double*)malloc(sizeof(double) * nt);
     for (int b = 0; b < B; ++b) {
         memset(smem, 0xff, sizeof(double) * nd);   // NaN-poison
+        memset(tmem, 0xff, sizeof(double) * nt);
         acmpc::Ctx<C> c;
-        c.S = smem, c.H = H, c.n = n, c.cfg = cfg, c.lane = acmpc::lane_iota();
-        double* raw = c.scan(0, 0);
+        c.S = smem, c.tm.p = tmem, c.H = H, c.n = n, c.cfg = cfg, c.lane = acmpc::lane_iota();
+        double* raw = c.scratch();
         memcpy(raw, paths + (size_t)b * 3 * H, sizeof(double) * 3 * (size_t)H);
         acmpc::InstanceOut o;
         o.controls = out->controls ? out->controls + (size_t)b * 2 * n : nullptr;
@@ -42,6 +45,7 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
         acmpc::solve_instance<C>(c, raw, offsets ? offsets[b] : 0.0, vmax ? vmax[b] : cfg->v_max, is_localised, o);
     }
     free(smem);
+    free(tmem);
 }
 
 }  // namespace
