@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -25,10 +26,19 @@ struct KernelParams {
     const double* paths;
     const double* offsets;
     const double* vmax;
+    double* vel;   // [B,n] speed profile: written by the speed kernel, read by the control kernel
     acmpc_outputs out;
     int32_t B;
     int32_t is_localised;
     int32_t use_tma;
+    // work queue of the persistent warps: a ticket counter that is never reset; the launch that starts at
+    // ticket `queue_base` hands out instance (ticket - queue_base) + (warps launched).  Launches of one
+    // handle are stream-ordered, and every solved instance draws exactly one ticket, so the host knows
+    // the base of the next launch without touching the device.
+    uint32_t* queue;
+    uint32_t queue_base;
+    uint32_t warps_launched;
+    int32_t persistent;   // 0: one instance per warp, grid = ceil(B/4) CTAs (warps of a CTA stay in phase)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -62,24 +72,85 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
             : "r"(bar)
             : "memory");
     }
+    // the barrier word is re-initialised for the warp's next instance
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+    __syncwarp();
 }
 
 constexpr int kWarpsPerCta = 4;   // one instance per warp; four warps share one tensor-memory allocation
 
 template <int C>
-__host__ __device__ constexpr size_t warp_smem_bytes()
+__host__ __device__ constexpr size_t warp_smem_bytes()   // control kernel
 {
     return sizeof(double) * (size_t)acmpc::Layout<C>::kDoubles + 16;   // + the warp's TMA mbarrier
 }
+template <int C>
+__host__ __device__ constexpr size_t warp_smem_bytes_speed()   // speed kernel
+{
+    return sizeof(double) * (size_t)acmpc::Layout<C>::kSpeedDoubles + 16;
+}
 
+__device__ __forceinline__ void stage_path(double* raw, const double* src, int H, bool use_tma, uint64_t* mbar, int lane)
+{
+    if (use_tma) {
+        tma_load_1d(raw, src, (uint32_t)(3 * H * sizeof(double)), mbar, lane);
+    } else {
+        for (int i = lane; i < 3 * H; i += 32) raw[i] = src[i];
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ acmpc::InstanceOut slice_outputs(const acmpc_outputs& g, int b, int H)
+{
+    const int n = H - 1;
+    acmpc::InstanceOut o;
+    o.controls = g.controls ? g.controls + (size_t)b * 2 * n : nullptr;
+    o.prediction = g.prediction ? g.prediction + (size_t)b * 2 * n : nullptr;
+    o.cum_time = g.cum_time ? g.cum_time + (size_t)b * n : nullptr;
+    o.states = g.states ? g.states + (size_t)b * 3 * H : nullptr;
+    o.v_ref = g.v_ref ? g.v_ref + (size_t)b * n : nullptr;
+    o.cost = g.cost ? g.cost + b : nullptr;
+    o.pri_res = g.pri_res ? g.pri_res + b : nullptr;
+    o.dua_res = g.dua_res ? g.dua_res + b : nullptr;
+    o.status = g.status ? g.status + b : nullptr;
+    o.status_speed = g.status_speed ? g.status_speed + b : nullptr;
+    o.iters = g.iters ? g.iters + (size_t)b * 2 : nullptr;
+    o.rho_updates = g.rho_updates ? g.rho_updates + (size_t)b * 2 : nullptr;
+    o.waypoints = g.waypoints ? g.waypoints + (size_t)b * 7 * n : nullptr;
+    return o;
+}
+
+// Kernel 1: waypoints + speed-profile QP, one warp per instance, registers only (plus 2 KB of scratch):
+// small code, high occupancy.  Hands the speed profile to kernel 2 through p.vel ([B,n], = out.v_ref when
+// the caller asked for that field).
+template <int C>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 3) acmpc_speed_kernel(const __grid_constant__ KernelParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kWarpsPerCta + warp;
+    if (b >= p.B) return;
+    const int H = p.cfg.horizon, n = H - 1;
+    acmpc::Ctx<C> c;
+    c.S = nullptr;
+    c.W = reinterpret_cast<double*>(smem_raw + (size_t)warp * warp_smem_bytes_speed<C>());
+    c.tm.a = 0;
+    c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(c.W + acmpc::Layout<C>::kSpeedDoubles);
+    stage_path(c.W, p.paths + (size_t)b * 3 * H, H, p.use_tma, mbar, lane);
+    const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
+    acmpc::speed_instance<C>(c, c.W, vmax, p.is_localised, p.vel + (size_t)b * n, slice_outputs(p.out, b, H));
+}
+
+// Kernel 2: control QP + unpack + rollout + cost.
 template <int C>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C == 2 ? 2 : 1)))
-    acmpc_step_kernel(const __grid_constant__ KernelParams p)
+    acmpc_control_kernel(const __grid_constant__ KernelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tmem_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * kWarpsPerCta + warp;
     // tensor memory: warp 0 allocates the CTA's columns, every warp then owns its 32-lane quarter of them
     constexpr uint32_t kCols = acmpc::Layout<C>::kTmemCols;
     if (warp == 0) {
@@ -91,40 +162,26 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C == 2 ? 2 :
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (b < p.B) {
+    // optionally persistent warps: the first instance is the warp's global index, further ones come from the
+    // queue, so a warp whose instance converges early does not idle behind its CTA's slowest one
+    for (int b = blockIdx.x * kWarpsPerCta + warp; b < p.B;) {
         const int H = p.cfg.horizon, n = H - 1;
         acmpc::Ctx<C> c;
         c.S = reinterpret_cast<double*>(smem_raw + (size_t)warp * warp_smem_bytes<C>());
+        c.W = c.S + acmpc::K_FIELDS * C * 32;
         c.tm.a = tmem_base + ((uint32_t)(32 * warp) << 16);
         c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
         uint64_t* mbar = reinterpret_cast<uint64_t*>(c.S + acmpc::Layout<C>::kDoubles);
         // the raw path slice lands in the scratch region: it is dead before the first factorisation
-        double* raw = c.scratch();
-        const double* src = p.paths + (size_t)b * 3 * H;
-        if (p.use_tma) {
-            tma_load_1d(raw, src, (uint32_t)(3 * H * sizeof(double)), mbar, lane);
-        } else {
-            for (int i = lane; i < 3 * H; i += 32) raw[i] = src[i];
-            __syncwarp();
-        }
-        acmpc::InstanceOut o;
-        const acmpc_outputs& g = p.out;
-        o.controls = g.controls ? g.controls + (size_t)b * 2 * n : nullptr;
-        o.prediction = g.prediction ? g.prediction + (size_t)b * 2 * n : nullptr;
-        o.cum_time = g.cum_time ? g.cum_time + (size_t)b * n : nullptr;
-        o.states = g.states ? g.states + (size_t)b * 3 * H : nullptr;
-        o.v_ref = g.v_ref ? g.v_ref + (size_t)b * n : nullptr;
-        o.cost = g.cost ? g.cost + b : nullptr;
-        o.pri_res = g.pri_res ? g.pri_res + b : nullptr;
-        o.dua_res = g.dua_res ? g.dua_res + b : nullptr;
-        o.status = g.status ? g.status + b : nullptr;
-        o.status_speed = g.status_speed ? g.status_speed + b : nullptr;
-        o.iters = g.iters ? g.iters + (size_t)b * 2 : nullptr;
-        o.rho_updates = g.rho_updates ? g.rho_updates + (size_t)b * 2 : nullptr;
-        o.waypoints = g.waypoints ? g.waypoints + (size_t)b * 7 * n : nullptr;
+        stage_path(c.W, p.paths + (size_t)b * 3 * H, H, p.use_tma, mbar, lane);
         const double offset = p.offsets ? p.offsets[b] : 0.0;
-        const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
-        acmpc::solve_instance<C>(c, raw, offset, vmax, p.is_localised, o);
+        acmpc::control_instance<C>(c, c.W, p.vel + (size_t)b * n, offset, slice_outputs(p.out, b, H));
+        if (!p.persistent) break;
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(p.queue, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        const uint32_t next = (ticket - p.queue_base) + p.warps_launched;
+        b = next < (uint32_t)p.B ? (int)next : p.B;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -152,11 +209,17 @@ struct acmpc_handle {
     acmpc_config cfg;
     int device;
     int sm_count;
+    int ctas_per_sm;
     std::string err;
     cudaStream_t stream;     // owned, used by the host entry point
     // device arena for the host entry point
     void* d_arena;
     size_t arena_bytes;
+    void* d_vel;             // speed-profile hand-over buffer of the device entry point (when v_ref is not requested)
+    size_t vel_bytes;
+    uint32_t* d_queue;       // ticket counter of the persistent warps (see KernelParams)
+    uint32_t queue_pos;      // its value once every launch issued so far has completed
+    int persistent;          // ACMPC_PERSISTENT=1: persistent warps + work queue (measured slower: see DESIGN.md)
     int last_launches, last_smem, last_threads, last_ipc;
 };
 
@@ -204,34 +267,80 @@ size_t smem_bytes_for(int H)   // dynamic shared memory per CTA
     }
 }
 
-const void* kernel_for(int H)
+int tmem_cols_for(int H)
 {
     switch (stages_per_lane(H)) {
-        case 1: return reinterpret_cast<const void*>(&acmpc_step_kernel<1>);
-        case 2: return reinterpret_cast<const void*>(&acmpc_step_kernel<2>);
-        case 3: return reinterpret_cast<const void*>(&acmpc_step_kernel<3>);
-        default: return reinterpret_cast<const void*>(&acmpc_step_kernel<4>);
+        case 1: return acmpc::Layout<1>::kTmemCols;
+        case 2: return acmpc::Layout<2>::kTmemCols;
+        case 3: return acmpc::Layout<3>::kTmemCols;
+        default: return acmpc::Layout<4>::kTmemCols;
     }
 }
 
+const void* kernel_for(int H)   // control kernel
+{
+    switch (stages_per_lane(H)) {
+        case 1: return reinterpret_cast<const void*>(&acmpc_control_kernel<1>);
+        case 2: return reinterpret_cast<const void*>(&acmpc_control_kernel<2>);
+        case 3: return reinterpret_cast<const void*>(&acmpc_control_kernel<3>);
+        default: return reinterpret_cast<const void*>(&acmpc_control_kernel<4>);
+    }
+}
+
+const void* speed_kernel_for(int H)
+{
+    switch (stages_per_lane(H)) {
+        case 1: return reinterpret_cast<const void*>(&acmpc_speed_kernel<1>);
+        case 2: return reinterpret_cast<const void*>(&acmpc_speed_kernel<2>);
+        case 3: return reinterpret_cast<const void*>(&acmpc_speed_kernel<3>);
+        default: return reinterpret_cast<const void*>(&acmpc_speed_kernel<4>);
+    }
+}
+
+size_t speed_smem_bytes_for(int H)
+{
+    switch (stages_per_lane(H)) {
+        case 1: return kWarpsPerCta * warp_smem_bytes_speed<1>();
+        case 2: return kWarpsPerCta * warp_smem_bytes_speed<2>();
+        case 3: return kWarpsPerCta * warp_smem_bytes_speed<3>();
+        default: return kWarpsPerCta * warp_smem_bytes_speed<4>();
+    }
+}
+
+// Two launches on `stream`: the speed-profile kernel, then the control kernel.  `d_vel` [B,n] is the
+// hand-over buffer between them.
 int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offsets, const double* d_vmax,
-           int is_localised, const acmpc_outputs* d_out, cudaStream_t stream)
+           int is_localised, const acmpc_outputs* d_out, double* d_vel, cudaStream_t stream)
 {
     KernelParams p;
     memset(&p, 0, sizeof(p));
     p.cfg = h->cfg;
     p.paths = d_paths, p.offsets = d_offsets, p.vmax = d_vmax;
     p.out = *d_out;
+    p.vel = d_vel;
     p.B = B, p.is_localised = is_localised ? 1 : 0;
     const int H = h->cfg.horizon;
     // TMA bulk copies need 16-byte aligned ends and a size that is a multiple of 16
     p.use_tma = ((3 * H * sizeof(double)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_paths) & 15) == 0);
     const size_t smem = smem_bytes_for(H);
     void* args[] = {&p};
-    const int ctas = (B + kWarpsPerCta - 1) / kWarpsPerCta;
+    // persistent CTAs: at most what the device holds at once (tensor memory / shared memory allow
+    // ctas_per_sm of them per SM), fewer for small batches
+    int ctas = (B + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int resident = h->sm_count * h->ctas_per_sm;
+    p.persistent = h->persistent;
+    if (p.persistent && ctas > resident) ctas = resident;
+    if (getenv("ACMPC_DEBUG")) fprintf(stderr, "acmpc launch: B=%d ctas=%d ctas_per_sm=%d sms=%d smem=%zu\n", B, ctas, h->ctas_per_sm, h->sm_count, smem);
+    p.queue = h->d_queue, p.queue_base = h->queue_pos, p.warps_launched = (uint32_t)(ctas * kWarpsPerCta);
+    if (p.persistent) h->queue_pos += (uint32_t)B;   // every solved instance draws one ticket
+    const int speed_ctas = (B + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (fail(h, cudaLaunchKernel(speed_kernel_for(H), dim3(speed_ctas), dim3(32 * kWarpsPerCta), args,
+                                 speed_smem_bytes_for(H), stream),
+             "speed kernel launch"))
+        return ACMPC_ERR_CUDA;
     if (fail(h, cudaLaunchKernel(kernel_for(H), dim3(ctas), dim3(32 * kWarpsPerCta), args, smem, stream), "kernel launch"))
         return ACMPC_ERR_CUDA;
-    h->last_launches = 1, h->last_smem = (int)smem, h->last_threads = 32 * kWarpsPerCta, h->last_ipc = kWarpsPerCta;
+    h->last_launches = 2, h->last_smem = (int)smem, h->last_threads = 32 * kWarpsPerCta, h->last_ipc = kWarpsPerCta;
     if (fail(h, cudaGetLastError(), "kernel launch")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
 }
@@ -287,13 +396,47 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
         return ACMPC_ERR_NO_DEVICE;
     }
     h->sm_count = prop.multiProcessorCount;
+    h->d_queue = nullptr, h->queue_pos = 0;
+    h->d_vel = nullptr, h->vel_bytes = 0;
+    {
+        const char* e = getenv("ACMPC_PERSISTENT");
+        h->persistent = (e && e[0] == '1') ? 1 : 0;
+    }
     const size_t smem = smem_bytes_for(cfg->horizon);
     if (smem > (size_t)prop.sharedMemPerBlockOptin ||
         fail(h, cudaFuncSetAttribute(kernel_for(cfg->horizon), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
              "cudaFuncSetAttribute") ||
+        fail(h, cudaFuncSetAttribute(speed_kernel_for(cfg->horizon), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)speed_smem_bytes_for(cfg->horizon)),
+             "cudaFuncSetAttribute(speed)") ||
+        fail(h, cudaFuncSetAttribute(kernel_for(cfg->horizon), cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared),
+             "cudaFuncSetAttribute(carveout)") ||
+        fail(h, cudaMalloc(&h->d_queue, sizeof(uint32_t)), "cudaMalloc(queue)") ||
+        fail(h, cudaMemset(h->d_queue, 0, sizeof(uint32_t)), "cudaMemset(queue)") ||
         fail(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        if (h->d_queue) cudaFree(h->d_queue);
         delete h;
         return ACMPC_ERR_CUDA;
+    }
+    // CTAs resident per SM = min over shared memory, registers and tensor memory (512 columns per SM).
+    // (cudaOccupancyMaxActiveBlocksPerMultiprocessor assumes the default carve-out and under-reports.)
+    {
+        cudaFuncAttributes fa;
+        if (fail(h, cudaFuncGetAttributes(&fa, kernel_for(cfg->horizon)), "cudaFuncGetAttributes")) {
+            cudaFree(h->d_queue);
+            cudaStreamDestroy(h->stream);
+            delete h;
+            return ACMPC_ERR_CUDA;
+        }
+        const size_t per_cta = smem + fa.sharedSizeBytes + prop.reservedSharedMemPerBlock;
+        const int by_smem = (int)(prop.sharedMemPerMultiprocessor / per_cta);
+        const int regs_per_cta = ((fa.numRegs + 7) / 8) * 8 * 32 * kWarpsPerCta;
+        const int by_regs = prop.regsPerMultiprocessor / regs_per_cta;
+        const int by_tmem = 512 / tmem_cols_for(cfg->horizon);
+        int r = by_smem < by_regs ? by_smem : by_regs;
+        if (by_tmem < r) r = by_tmem;
+        h->ctas_per_sm = r < 1 ? 1 : r;
     }
     *out = h;
     return ACMPC_OK;
@@ -304,6 +447,8 @@ int32_t acmpc_destroy(acmpc_handle* h)
     if (!h) return ACMPC_OK;
     cudaSetDevice(h->device);
     if (h->d_arena) cudaFree(h->d_arena);
+    if (h->d_queue) cudaFree(h->d_queue);
+    if (h->d_vel) cudaFree(h->d_vel);
     cudaStreamDestroy(h->stream);
     delete h;
     return ACMPC_OK;
@@ -332,7 +477,21 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
     }
     if (B == 0) return ACMPC_OK;
     if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
-    return launch(h, B, d_paths, d_offsets, d_vmax, is_localised, d_out, static_cast<cudaStream_t>(stream));
+    double* d_vel = d_out->v_ref;
+    if (!d_vel) {   // the caller did not ask for v_ref: hand over through a scratch buffer owned by the handle
+        const size_t need = (size_t)B * (h->cfg.horizon - 1) * sizeof(double);
+        if (need > h->vel_bytes) {
+            if (h->d_vel) {
+                if (fail(h, cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return ACMPC_ERR_CUDA;
+                cudaFree(h->d_vel);
+            }
+            h->d_vel = nullptr, h->vel_bytes = 0;
+            if (fail(h, cudaMalloc(&h->d_vel, need), "cudaMalloc(vel)")) return ACMPC_ERR_CUDA;
+            h->vel_bytes = need;
+        }
+        d_vel = static_cast<double*>(h->d_vel);
+    }
+    return launch(h, B, d_paths, d_offsets, d_vmax, is_localised, d_out, d_vel, static_cast<cudaStream_t>(stream));
 }
 
 int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, const double* offsets,
@@ -392,7 +551,8 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
     if (out->waypoints) d.waypoints = reinterpret_cast<double*>(base + o_wp);
     int rc = launch(h, B, reinterpret_cast<const double*>(base + o_paths),
                     offsets ? reinterpret_cast<const double*>(base + o_off) : nullptr,
-                    vmax ? reinterpret_cast<const double*>(base + o_vmax) : nullptr, is_localised, &d, s);
+                    vmax ? reinterpret_cast<const double*>(base + o_vmax) : nullptr, is_localised, &d,
+                    reinterpret_cast<double*>(base + o_vr), s);
     if (rc != ACMPC_OK) return rc;
 #define ACMPC_D2H(field, bytes)                                                                              \
     if (out->field &&                                                                                         \

@@ -73,7 +73,7 @@ enum : int {
     NC_N = 0, NC_SI = 9
 };
 enum : int {
-    F_XS = 0, F_YS, F_PSI, F_VEL,   // ReferencePath rows needed after the solves (paths.py:4-72)
+    F_XS = 0, F_YS, F_PSI,          // ReferencePath rows needed by the rollout (paths.py:4-72)
     K_P,                            // 5: diagonal of P
     K_DI = K_P + 5,                 // 5: 1/D
     K_EEI = K_DI + 5,               // 3: 1/E of the equality block
@@ -88,7 +88,8 @@ enum : int {
 template <int C>
 struct Layout {
     static constexpr int kScratch = ((W_FIELDS * C > kLevels * 9) ? W_FIELDS * C : kLevels * 9) * 32;
-    static constexpr int kDoubles = K_FIELDS * C * 32 + kScratch;   // shared memory per warp
+    static constexpr int kDoubles = K_FIELDS * C * 32 + kScratch;   // shared memory per warp, control phase
+    static constexpr int kSpeedDoubles = (2 * C * 32 > 3 * 32 * C) ? 2 * C * 32 : 3 * 32 * C;   // speed phase: raw path / LDL work
     static constexpr int kTmemDoubles = T_STRIDE * C;               // tensor memory per lane
     static constexpr int kTmemCols = (2 * kTmemDoubles <= 128) ? 128 : ((2 * kTmemDoubles <= 256) ? 256 : 512);
 };
@@ -221,15 +222,16 @@ AC_DEV VD support(const VD& dy, const VD& lo, const VD& hi)
 // ------------------------------------------------------------------------------------------------
 template <int C>
 struct Ctx {
-    double* S;   // base of this instance's (warp's) shared-memory block
-    Tm tm;       // base of this instance's tensor-memory block (the warp's lane quarter)
+    double* S;   // this instance's (warp's) cold per-stage fields in shared memory (control phase only)
+    double* W;   // this instance's scratch / scan region in shared memory
+    Tm tm;       // base of this instance's tensor-memory block (the warp's lane quarter; control phase only)
     int H, n;
     const acmpc_config* cfg;
     VI lane;
     AC_MEM double* col(int f, int j) const { return S + (f * C + j) * 32; }
     AC_MEM VD ld(int f, int j) const { return ld_lane(col(f, j)); }
     AC_MEM void st(int f, int j, const VD& v) const { st_lane(col(f, j), v); }
-    AC_MEM double* scratch() const { return S + K_FIELDS * C * 32; }
+    AC_MEM double* scratch() const { return W; }
     AC_MEM double* wcol(int f, int j) const { return scratch() + (f * C + j) * 32; }
     AC_MEM double* scan(int lvl, int e) const { return scratch() + (lvl * 9 + e) * 32; }
     AC_MEM VI stage(int j) const { return lane * C + j; }
@@ -1445,29 +1447,28 @@ struct InstanceOut {
     double* waypoints;
 };
 
+// Phase 1 of the step: waypoints + speed-profile QP (spatial_mpc.py:176-184).  Uses registers and the scratch
+// region only.  `vel_out` [n] always receives the profile (zeros unless the QP status is "solved",
+// spatial_mpc.py:115-122); it is the hand-over to phase 2.
 template <int C>
-AC_DEV void solve_instance(const Ctx<C>& c, const double* raw_path, double offset, double v_max_live,
-                           int localised, const InstanceOut& o)
+AC_DEV void speed_instance(const Ctx<C>& c, const double* raw_path, double v_max_live, int localised,
+                           double* vel_out, const InstanceOut& o)
 {
-    const int n = c.n, H = c.H;
+    const int n = c.n;
     PathRegs<C> path;
     build_waypoints<C>(c, raw_path, path);
     warp_sync();
-    SolveInfo si, ci;
+    SolveInfo si;
     VD vel[C];
-    {
-        SpeedQP<C> sq(c);
-        sq.assemble_and_scale(path, v_max_live, localised);
-        sq.solve(si, vel);
-        // spatial_mpc.py:115-122: velocities are assigned only when the status is "solved"
-        AC_UNROLL
-        for (int j = 0; j < C; ++j) vel[j] = (si.status == ACMPC_SOLVED) ? vsel(vi_lt(c.stage(j), n), vel[j], VD(0.0)) : VD(0.0);
-    }
+    SpeedQP<C> sq(c);
+    sq.assemble_and_scale(path, v_max_live, localised);
+    sq.solve(si, vel);
     AC_UNROLL
     for (int j = 0; j < C; ++j) {
         VI st = c.stage(j);
         VB ok = vi_lt(st, n);
-        c.st(F_XS, j, path.xs[j]), c.st(F_YS, j, path.ys[j]), c.st(F_PSI, j, path.psi[j]), c.st(F_VEL, j, vel[j]);
+        vel[j] = (si.status == ACMPC_SOLVED) ? vsel(ok, vel[j], VD(0.0)) : VD(0.0);
+        st_idx_if(ok, vel_out, st, vel[j]);
         if (o.waypoints) {
             st_idx_if(ok, o.waypoints + 0 * n, st, path.xs[j]);
             st_idx_if(ok, o.waypoints + 1 * n, st, path.ys[j]);
@@ -1477,7 +1478,32 @@ AC_DEV void solve_instance(const Ctx<C>& c, const double* raw_path, double offse
             st_idx_if(ok, o.waypoints + 5 * n, st, path.wid[j]);
             st_idx_if(ok, o.waypoints + 6 * n, st, vel[j]);
         }
-        if (o.v_ref) st_idx_if(ok, o.v_ref, st, vel[j]);
+        if (o.v_ref && o.v_ref != vel_out) st_idx_if(ok, o.v_ref, st, vel[j]);
+    }
+    AC_LANE0
+    {
+        if (o.status_speed) *o.status_speed = si.status;
+        if (o.iters) o.iters[0] = si.iter;
+        if (o.rho_updates) o.rho_updates[0] = si.rho_updates;
+    }
+}
+
+// Phase 2: control QP, unpack, rollout, cost (spatial_mpc.py:186-212).  The waypoints are rebuilt from the
+// staged raw path (cheaper than handing six rows per stage over); `vel_in` [n] is phase 1's profile.
+template <int C>
+AC_DEV void control_instance(const Ctx<C>& c, const double* raw_path, const double* vel_in, double offset,
+                             const InstanceOut& o)
+{
+    const int n = c.n, H = c.H;
+    PathRegs<C> path;
+    build_waypoints<C>(c, raw_path, path);
+    warp_sync();
+    SolveInfo ci;
+    VD vel[C];
+    AC_UNROLL
+    for (int j = 0; j < C; ++j) {
+        vel[j] = ld_idx_if(vi_lt(c.stage(j), n), vel_in, c.stage(j), 0.0);
+        c.st(F_XS, j, path.xs[j]), c.st(F_YS, j, path.ys[j]), c.st(F_PSI, j, path.psi[j]);
     }
     ControlQP<C> cq(c);
     cq.setup(path, vel, offset);
@@ -1515,9 +1541,8 @@ AC_DEV void solve_instance(const Ctx<C>& c, const double* raw_path, double offse
         if (o.pri_res) *o.pri_res = ci.pri_res;
         if (o.dua_res) *o.dua_res = ci.dua_res;
         if (o.status) *o.status = ci.status;
-        if (o.status_speed) *o.status_speed = si.status;
-        if (o.iters) o.iters[0] = si.iter, o.iters[1] = ci.iter;
-        if (o.rho_updates) o.rho_updates[0] = si.rho_updates, o.rho_updates[1] = ci.rho_updates;
+        if (o.iters) o.iters[1] = ci.iter;
+        if (o.rho_updates) o.rho_updates[1] = ci.rho_updates;
     }
 }
 

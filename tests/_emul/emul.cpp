@@ -21,11 +21,13 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
     const size_t nt = (size_t)acmpc::Layout<C>::kTmemDoubles * 32;   // tensor-memory model: [double column][lane]
     double* smem = (double*)malloc(sizeof(double) * nd);
     double* tmem = (double*)malloc(sizeof(double) * nt);
+    double* vel = (double*)malloc(sizeof(double) * (size_t)H);
     for (int b = 0; b < B; ++b) {
         memset(smem, 0xff, sizeof(double) * nd);   // NaN-poison
         memset(tmem, 0xff, sizeof(double) * nt);
         acmpc::Ctx<C> c;
-        c.S = smem, c.tm.p = tmem, c.H = H, c.n = n, c.cfg = cfg, c.lane = acmpc::lane_iota();
+        c.S = smem, c.W = smem + acmpc::K_FIELDS * C * 32, c.tm.p = tmem, c.H = H, c.n = n, c.cfg = cfg;
+        c.lane = acmpc::lane_iota();
         double* raw = c.scratch();
         memcpy(raw, paths + (size_t)b * 3 * H, sizeof(double) * 3 * (size_t)H);
         acmpc::InstanceOut o;
@@ -42,10 +44,15 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
         o.iters = out->iters ? out->iters + (size_t)b * 2 : nullptr;
         o.rho_updates = out->rho_updates ? out->rho_updates + (size_t)b * 2 : nullptr;
         o.waypoints = out->waypoints ? out->waypoints + (size_t)b * 7 * n : nullptr;
-        acmpc::solve_instance<C>(c, raw, offsets ? offsets[b] : 0.0, vmax ? vmax[b] : cfg->v_max, is_localised, o);
+        // the two phases are two kernels in the product; the hand-over is the speed profile
+        acmpc::speed_instance<C>(c, raw, vmax ? vmax[b] : cfg->v_max, is_localised, vel, o);
+        memset(smem, 0xff, sizeof(double) * nd);
+        memcpy(raw, paths + (size_t)b * 3 * H, sizeof(double) * 3 * (size_t)H);
+        acmpc::control_instance<C>(c, raw, vel, offsets ? offsets[b] : 0.0, o);
     }
     free(smem);
     free(tmem);
+    free(vel);
 }
 
 }  // namespace
