@@ -219,7 +219,7 @@ struct acmpc_handle {
     size_t vel_bytes;
     uint32_t* d_queue;       // ticket counter of the persistent warps (see KernelParams)
     uint32_t queue_pos;      // its value once every launch issued so far has completed
-    int persistent;          // ACMPC_PERSISTENT=1: persistent warps + work queue (measured slower: see DESIGN.md)
+    int persistent;          // persistent control-kernel warps + work queue (ACMPC_PERSISTENT=0 switches it off)
     int last_launches, last_smem, last_threads, last_ipc;
 };
 
@@ -400,7 +400,7 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
     h->d_vel = nullptr, h->vel_bytes = 0;
     {
         const char* e = getenv("ACMPC_PERSISTENT");
-        h->persistent = (e && e[0] == '1') ? 1 : 0;
+        h->persistent = (e && e[0] == '0') ? 0 : 1;
     }
     const size_t smem = smem_bytes_for(cfg->horizon);
     if (smem > (size_t)prop.sharedMemPerBlockOptin ||
