@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTED = [
     "acmpc_abi_version", "acmpc_default_config", "acmpc_create", "acmpc_destroy", "acmpc_last_error",
     "acmpc_warm_stride", "acmpc_solve_batch_device", "acmpc_solve_batch_host", "acmpc_last_launch_info",
-    "acmpc_fp64_peak_tflops",
+    "acmpc_fp64_peak_tflops", "acmpc_set_profiling", "acmpc_collect_kernel_ms",
 ]
 
 RC_NAMES = {0: "ACMPC_OK", 1: "ACMPC_ERR_INVALID", 2: "ACMPC_ERR_CUDA", 3: "ACMPC_ERR_NO_DEVICE"}
@@ -130,6 +130,10 @@ def load() -> C.CDLL:
     L.acmpc_last_launch_info.restype = C.c_int32
     L.acmpc_fp64_peak_tflops.argtypes = [C.c_int32, dp]
     L.acmpc_fp64_peak_tflops.restype = C.c_int32
+    L.acmpc_set_profiling.argtypes = [vp, C.c_int32]
+    L.acmpc_set_profiling.restype = C.c_int32
+    L.acmpc_collect_kernel_ms.argtypes = [vp, dp, dp, C.POINTER(C.c_int32)]
+    L.acmpc_collect_kernel_ms.restype = C.c_int32
     _lib = L
     return L
 

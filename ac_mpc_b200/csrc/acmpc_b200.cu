@@ -78,6 +78,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
     __syncwarp();
 }
 
+constexpr int kEventRing = 256;
 constexpr int kWarpsPerCta = 4;   // one instance per warp; four warps share one tensor-memory allocation
 
 template <int C>
@@ -219,6 +220,9 @@ struct acmpc_handle {
     size_t vel_bytes;
     uint32_t* d_queue;       // ticket counter of the persistent warps (see KernelParams)
     uint32_t queue_pos;      // its value once every launch issued so far has completed
+    int profiling;           // record events around the two kernels (acmpc_set_profiling)
+    cudaEvent_t* ev;         // 3 * kEventRing events
+    int ev_head, ev_count;
     int persistent;          // persistent control-kernel warps + work queue (ACMPC_PERSISTENT=0 switches it off)
     int last_launches, last_smem, last_threads, last_ipc;
 };
@@ -333,13 +337,22 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     if (getenv("ACMPC_DEBUG")) fprintf(stderr, "acmpc launch: B=%d ctas=%d ctas_per_sm=%d sms=%d smem=%zu\n", B, ctas, h->ctas_per_sm, h->sm_count, smem);
     p.queue = h->d_queue, p.queue_base = h->queue_pos, p.warps_launched = (uint32_t)(ctas * kWarpsPerCta);
     if (p.persistent) h->queue_pos += (uint32_t)B;   // every solved instance draws one ticket
+    cudaEvent_t* ev = nullptr;
+    if (h->profiling && h->ev) {
+        ev = h->ev + 3 * h->ev_head;
+        h->ev_head = (h->ev_head + 1) % kEventRing;
+        if (h->ev_count < kEventRing) ++h->ev_count;
+        cudaEventRecord(ev[0], stream);
+    }
     const int speed_ctas = (B + kWarpsPerCta - 1) / kWarpsPerCta;
     if (fail(h, cudaLaunchKernel(speed_kernel_for(H), dim3(speed_ctas), dim3(32 * kWarpsPerCta), args,
                                  speed_smem_bytes_for(H), stream),
              "speed kernel launch"))
         return ACMPC_ERR_CUDA;
+    if (ev) cudaEventRecord(ev[1], stream);
     if (fail(h, cudaLaunchKernel(kernel_for(H), dim3(ctas), dim3(32 * kWarpsPerCta), args, smem, stream), "kernel launch"))
         return ACMPC_ERR_CUDA;
+    if (ev) cudaEventRecord(ev[2], stream);
     h->last_launches = 2, h->last_smem = (int)smem, h->last_threads = 32 * kWarpsPerCta, h->last_ipc = kWarpsPerCta;
     if (fail(h, cudaGetLastError(), "kernel launch")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
@@ -398,6 +411,7 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
     h->sm_count = prop.multiProcessorCount;
     h->d_queue = nullptr, h->queue_pos = 0;
     h->d_vel = nullptr, h->vel_bytes = 0;
+    h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
     {
         const char* e = getenv("ACMPC_PERSISTENT");
         h->persistent = (e && e[0] == '0') ? 0 : 1;
@@ -449,6 +463,10 @@ int32_t acmpc_destroy(acmpc_handle* h)
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->d_queue) cudaFree(h->d_queue);
     if (h->d_vel) cudaFree(h->d_vel);
+    if (h->ev) {
+        for (int i = 0; i < 3 * kEventRing; ++i) cudaEventDestroy(h->ev[i]);
+        delete[] h->ev;
+    }
     cudaStreamDestroy(h->stream);
     delete h;
     return ACMPC_OK;
@@ -486,6 +504,7 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
                 cudaFree(h->d_vel);
             }
             h->d_vel = nullptr, h->vel_bytes = 0;
+    h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
             if (fail(h, cudaMalloc(&h->d_vel, need), "cudaMalloc(vel)")) return ACMPC_ERR_CUDA;
             h->vel_bytes = need;
         }
@@ -584,6 +603,43 @@ int32_t acmpc_last_launch_info(const acmpc_handle* h, int32_t* n_launches, int32
     if (smem_bytes) *smem_bytes = h->last_smem;
     if (threads_per_cta) *threads_per_cta = h->last_threads;
     if (instances_per_cta) *instances_per_cta = h->last_ipc;
+    return ACMPC_OK;
+}
+
+int32_t acmpc_set_profiling(acmpc_handle* h, int32_t on)
+{
+    if (!h) return ACMPC_ERR_INVALID;
+    if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    if (on && !h->ev) {
+        h->ev = new (std::nothrow) cudaEvent_t[3 * kEventRing];
+        if (!h->ev) return ACMPC_ERR_INVALID;
+        for (int i = 0; i < 3 * kEventRing; ++i)
+            if (fail(h, cudaEventCreate(&h->ev[i]), "cudaEventCreate")) return ACMPC_ERR_CUDA;
+    }
+    h->profiling = on ? 1 : 0;
+    h->ev_head = 0, h->ev_count = 0;
+    return ACMPC_OK;
+}
+
+int32_t acmpc_collect_kernel_ms(acmpc_handle* h, double* speed_ms, double* control_ms, int32_t* launches)
+{
+    if (!h) return ACMPC_ERR_INVALID;
+    double s = 0.0, c = 0.0;
+    const int cnt = h->ev_count;
+    for (int k = 0; k < cnt; ++k) {
+        const int slot = ((h->ev_head - 1 - k) % kEventRing + kEventRing) % kEventRing;
+        cudaEvent_t* ev = h->ev + 3 * slot;
+        if (fail(h, cudaEventSynchronize(ev[2]), "cudaEventSynchronize")) return ACMPC_ERR_CUDA;
+        float a = 0.f, b = 0.f;
+        if (fail(h, cudaEventElapsedTime(&a, ev[0], ev[1]), "cudaEventElapsedTime") ||
+            fail(h, cudaEventElapsedTime(&b, ev[1], ev[2]), "cudaEventElapsedTime"))
+            return ACMPC_ERR_CUDA;
+        s += a, c += b;
+    }
+    if (speed_ms) *speed_ms = s;
+    if (control_ms) *control_ms = c;
+    if (launches) *launches = cnt;
+    h->ev_head = 0, h->ev_count = 0;
     return ACMPC_OK;
 }
 

@@ -710,12 +710,17 @@ struct SpeedQP {
         // `pass` 0 is an ADMM iteration, passes 1 and 2 are those two extra checks: check() has ONE call site.
         int pass = 0;
         bool checked = false, adapt = false, last = false;
+        // countdowns instead of iter % interval (a runtime integer division per test)
+        int to_check = g.check_termination > 0 ? g.check_termination : -1;
+        int to_adapt = (g.adaptive_rho && g.adaptive_rho_interval > 0) ? g.adaptive_rho_interval : -1;
         for (;;) {
             if (pass == 0) {
                 ++iter;
-                checked = (g.check_termination > 0 && iter % g.check_termination == 0);
+                checked = (--to_check == 0);
+                if (checked) to_check = g.check_termination;
+                adapt = (--to_adapt == 0);
+                if (adapt) to_adapt = g.adaptive_rho_interval;
                 last = iter >= g.max_iter;
-                adapt = g.adaptive_rho && g.adaptive_rho_interval > 0 && iter % g.adaptive_rho_interval == 0;
                 iterate(alpha, sigma);
                 if (checked || adapt || last) compute_norms(N);
             }
@@ -1393,12 +1398,17 @@ struct ControlQP {
         // same pass structure as SpeedQP::solve
         int pass = 0;
         bool checked = false, adapt = false, last = false;
+        // countdowns instead of iter % interval (a runtime integer division per test)
+        int to_check = g.check_termination > 0 ? g.check_termination : -1;
+        int to_adapt = (g.adaptive_rho && g.adaptive_rho_interval > 0) ? g.adaptive_rho_interval : -1;
         for (;;) {
             if (pass == 0) {
                 ++iter;
-                checked = (g.check_termination > 0 && iter % g.check_termination == 0);
+                checked = (--to_check == 0);
+                if (checked) to_check = g.check_termination;
+                adapt = (--to_adapt == 0);
+                if (adapt) to_adapt = g.adaptive_rho_interval;
                 last = iter >= g.max_iter;
-                adapt = g.adaptive_rho && g.adaptive_rho_interval > 0 && iter % g.adaptive_rho_interval == 0;
                 iterate(checked || last);
                 if (checked || adapt || last) compute_norms(N);
             }

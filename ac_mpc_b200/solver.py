@@ -85,6 +85,16 @@ class BatchedMPC:
         self._check(self._lib.acmpc_last_launch_info(self._handle(), *[C.byref(v) for v in vals]))
         return dict(zip(("launches", "smem_bytes", "threads_per_cta", "instances_per_cta"), (v.value for v in vals)))
 
+    def set_profiling(self, on: bool):
+        """Record CUDA events around the two kernels of every following launch (acmpc_set_profiling)."""
+        self._check(self._lib.acmpc_set_profiling(self._handle(), int(bool(on))))
+
+    def collect_kernel_ms(self) -> Dict[str, float]:
+        """Summed device times of the speed-profile and control kernels since the last collect."""
+        s, c, k = C.c_double(), C.c_double(), C.c_int32()
+        self._check(self._lib.acmpc_collect_kernel_ms(self._handle(), C.byref(s), C.byref(c), C.byref(k)))
+        return {"speed_ms": s.value, "control_ms": c.value, "launches": k.value}
+
     # -- host buffers ---------------------------------------------------------------------------
     def alloc_host_outputs(self, B: int, fields=None, pinned: bool = False):
         """numpy arrays (optionally views of pinned torch tensors) for every requested field."""

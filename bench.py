@@ -58,14 +58,15 @@ def config_kwargs(track: str, H: int):
                 r_term=[1e-2, 10.0], final_cost=[1.0, 0.0, 0.1], input_v_min=r["v_min"], input_v_max=84.0)
 
 
-def flops_per_batch(H: int, iters: np.ndarray, rho_updates: np.ndarray) -> float:
+def flops_per_batch(H: int, iters: np.ndarray, rho_updates: np.ndarray) -> tuple[float, float]:
     """Algorithmic FP64 flop model of SURVEY.md 8(d) / DESIGN.md, summed over the kernel-reported
-    per-instance ADMM iteration counts (column 0 speed QP, column 1 control QP)."""
+    per-instance ADMM iteration counts (column 0 speed QP, column 1 control QP).  Returns the flops of the
+    (speed-profile kernel, control kernel): waypoints + speed QP / assembly + Ruiz + control QP + rollout."""
     Ks, Kc = iters[:, 0].astype(np.float64), iters[:, 1].astype(np.float64)
     Fs, Fc = 1.0 + rho_updates[:, 0], 1.0 + rho_updates[:, 1]
-    per = (Kc * (319 * H - 70) + (Kc / 25.0) * (96 * H + 12 * 13 * H) + Fc * 300 * H + 40 * (16 * H - 10)
-           + Ks * 45 * H + Fs * 10 * H + 150 * H)
-    return float(per.sum())
+    control = Kc * (319 * H - 70) + (Kc / 25.0) * (96 * H + 12 * 13 * H) + Fc * 300 * H + 40 * (16 * H - 10) + 100 * H
+    speed = Ks * 45 * H + Fs * 10 * H + 50 * H
+    return float(speed.sum()), float(control.sum())
 
 
 def bytes_per_solve(H: int, fields) -> tuple[int, int]:
@@ -237,6 +238,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    mpc.set_profiling(True)        # events around each of the two kernels, on the launching stream
     for i in range(K):
         flush.fill_(i & 0xFF)                  # L2 flush between timed iterations (outside the events)
         ev[i][0].record()
@@ -247,6 +249,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             dist.all_gather_into_tensor(gathered, packed)
         ev[i][1].record()
     torch.cuda.synchronize()
+    per_kernel = mpc.collect_kernel_ms()
+    mpc.set_profiling(False)
     if world > 1:
         dist.barrier()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -286,11 +290,15 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     if rank != 0:
         return
     iters, rhou = h_out["iters"], h_out["rho_updates"]
-    flops = flops_per_batch(H, iters, rhou)
+    flops_speed, flops_control = flops_per_batch(H, iters, rhou)
+    flops = flops_speed + flops_control
     peaks, how = measured_peaks()
     fp64_peak = fp64_peak_tflops(local_rank)
     k_s = kernel_ms * 1e-3
-    achieved_tf = flops / k_s / 1e12
+    nl = max(per_kernel["launches"], 1)
+    control_ms, speed_ms = per_kernel["control_ms"] / nl, per_kernel["speed_ms"] / nl
+    # roofline of the dominant kernel (the control kernel): its algorithmic flops / its own device time
+    achieved_tf = flops_control / (control_ms * 1e-3) / 1e12
     hbm_gbs = B * (bin_ + bout) / k_s / 1e9
     traffic = recorded_traffic()
 
@@ -331,8 +339,14 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                 "d2h_bytes_per_step": B * bout, "api": "SpatialMPC.get_control_batch -> acmpc_solve_batch_host"},
         "gpu_launches": K * mpc.launch_info()["launches"],
         "kernel_ms": kernel_ms,
-        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp64_peak, "traffic": traffic,
+        "kernels": {"acmpc_speed_kernel": {"ms": speed_ms, "flops_per_launch": flops_speed,
+                                           "tflops": flops_speed / (speed_ms * 1e-3) / 1e12},
+                    "acmpc_control_kernel": {"ms": control_ms, "flops_per_launch": flops_control,
+                                             "tflops": flops_control / (control_ms * 1e-3) / 1e12},
+                    "timed": f"CUDA events on the launching stream around each kernel, mean of {nl} launches"},
+        "roofline": {"kernel": "acmpc_control_kernel", "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak,
+                     "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
+                     "whole_step": {"achieved": flops / k_s / 1e12, "frac": flops / k_s / 1e12 / fp64_peak},
                      "peak_source": "DFMA micro-benchmark in this run (acmpc_fp64_peak_tflops); "
                                     "MEASURED_PEAKS.json has no FP64 figure",
                      "flops_per_solve": flops / B,

@@ -113,7 +113,11 @@ int64_t acmpc_warm_stride(const acmpc_handle *h);
  *   is_localised: get_control arg 2
  *   d_warm    NULL = cold start (x=z=y=0, rho=cfg.rho) ; else [B, acmpc_warm_stride] bytes, read
  *             when warm_valid != 0 and always rewritten (the reference's persistent OSQP objects)
- *   stream    cudaStream_t (NULL = default stream).  Asynchronous: no host sync inside. */
+ *   stream    cudaStream_t (NULL = default stream).  Asynchronous: no host sync inside (except when the
+ *             internal speed-profile hand-over buffer has to grow: first call, or a larger B, with
+ *             d_out->v_ref == NULL).  Calls on one handle must be stream-ordered with each other (the
+ *             reference object is single-threaded): the work queue of the persistent warps
+ *             is per handle. */
 int32_t acmpc_solve_batch_device(acmpc_handle *h, int32_t B, const double *d_paths,
                                  const double *d_offsets, const double *d_vmax,
                                  int32_t is_localised, void *d_warm, int32_t warm_valid,
@@ -126,9 +130,17 @@ int32_t acmpc_solve_batch_host(acmpc_handle *h, int32_t B, const double *paths,
                                const double *offsets, const double *vmax, int32_t is_localised,
                                int32_t keep_warm, const acmpc_outputs *out);
 
-/* Counters of the last launch: kernel launches issued and dynamic shared memory per CTA. */
+/* Counters of the last call: kernel launches issued (2: speed-profile kernel + control kernel), dynamic shared
+ * memory per CTA of the control kernel, threads per CTA, instances per CTA. */
 int32_t acmpc_last_launch_info(const acmpc_handle *h, int32_t *n_launches, int32_t *smem_bytes,
                                int32_t *threads_per_cta, int32_t *instances_per_cta);
+
+/* Per-kernel device times.  acmpc_set_profiling(h, 1) makes every following launch record CUDA events on its
+ * stream around the two kernels of the step (speed-profile kernel, control kernel); acmpc_collect_kernel_ms
+ * synchronises on them and returns the summed durations and the number of launches since the previous
+ * collect (at most 256 launches are remembered).  Off by default: it costs three event records per launch. */
+int32_t acmpc_set_profiling(acmpc_handle *h, int32_t on);
+int32_t acmpc_collect_kernel_ms(acmpc_handle *h, double *speed_ms, double *control_ms, int32_t *launches);
 
 /* FP64 FMA micro-benchmark (dependent-chain-free DFMA loop on every SM): the roofline
  * denominator for this path, MEASURED_PEAKS.json has no FP64 figure.  Returns TFLOP/s. */
