@@ -3,7 +3,7 @@
 
 In the reference this class also linearises the model on the host (dynamics.py:65-103); here the
 linearisation, the t2s initial-state transform and the s2t rollout all happen inside the CUDA kernel
-(ac_mpc_b200/csrc/mpc_body.cuh: ControlQP::assemble / solve_instance), so the object only carries the
+(ac_mpc_b200/csrc/mpc_warp.cuh: ControlQP::setup / control_instance), so the object only carries the
 constants that become fields of `acmpc_config`."""
 from __future__ import annotations
 

@@ -1,4 +1,4 @@
-"""CPU-only: the arithmetic of the CUDA kernel body (ac_mpc_b200/csrc/mpc_body.cuh compiled by g++ with
+"""CPU-only: the arithmetic of the CUDA kernel body (ac_mpc_b200/csrc/mpc_warp.cuh compiled by g++ with
 32 lock-step lanes, tests/_emul) against the golden vectors of the reference Python.  This does not exercise the
 32-lane execution -- tests/test_gpu_parity.py does, on the B200."""
 import numpy as np
