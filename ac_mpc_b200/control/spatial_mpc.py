@@ -69,21 +69,23 @@ class SpatialMPC:
         return self._solver
 
     def get_control_batch(self, reference_paths, offsets=None, v_max=None, is_localised: bool = False,
-                          fields=None, out=None) -> Dict[str, np.ndarray]:
+                          fields=None, out=None, keep_warm: bool = False) -> Dict[str, np.ndarray]:
         """B independent MPC steps: reference_paths (B,H,3), offsets (B,), v_max (B,) -> dict of arrays
-        (fields of `acmpc_outputs`).  Cold start per instance.  `out`: optional preallocated (e.g. pinned)
-        host arrays from `BatchedMPC.alloc_host_outputs`."""
+        (fields of `acmpc_outputs`).  Cold start per instance unless keep_warm (then slot b of consecutive
+        calls is one persistent solver object, like the reference's).  `out`: optional preallocated (e.g.
+        pinned) host arrays from `BatchedMPC.alloc_host_outputs`."""
         solver = self._batched()
         paths = np.ascontiguousarray(reference_paths, dtype=np.float64)
         B = paths.shape[0]
         if v_max is None:
             v_max = np.full(B, float(self.speed_profile_constraints["v_max"]))
-        return solver.solve_host(paths, offsets, v_max, is_localised, out=out, fields=fields)
+        return solver.solve_host(paths, offsets, v_max, is_localised, out=out, fields=fields, keep_warm=keep_warm)
 
     def get_control(self, reference_path: np.ndarray, is_localised: bool = False, offset: float = 0.0):
         """One MPC step; signature and side effects of spatial_mpc.py:170-217."""
         path = np.ascontiguousarray(reference_path, dtype=np.float64)[None]
-        out = self.get_control_batch(path, np.array([float(offset)]), None, is_localised)
+        # the reference keeps its OSQP objects between calls (warm start, carried rho): so does the handle
+        out = self.get_control_batch(path, np.array([float(offset)]), None, is_localised, keep_warm=True)
         n = self.MPC_horizon - 1
         status, status_speed = int(out["status"][0]), int(out["status_speed"][0])
         self.last_info = dict(status=_capi.STATUS_STRINGS.get(status, str(status)),

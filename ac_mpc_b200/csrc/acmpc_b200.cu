@@ -27,6 +27,8 @@ struct KernelParams {
     const double* offsets;
     const double* vmax;
     double* vel;   // [B,n] speed profile: written by the speed kernel, read by the control kernel
+    double* warm;  // NULL or [B, Layout<C>::kWarmDoubles] warm-start records (read when use_warm, always rewritten)
+    int32_t use_warm;
     acmpc_outputs out;
     int32_t B;
     int32_t is_localised;
@@ -141,7 +143,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 3) acmpc_speed_kernel(const
     uint64_t* mbar = reinterpret_cast<uint64_t*>(c.W + acmpc::Layout<C>::kSpeedDoubles);
     stage_path(c.W, p.paths + (size_t)b * 3 * H, H, p.use_tma, mbar, lane);
     const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
-    acmpc::speed_instance<C>(c, c.W, vmax, p.is_localised, p.vel + (size_t)b * n, slice_outputs(p.out, b, H));
+    double* wrec = p.warm ? p.warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;
+    acmpc::speed_instance<C>(c, c.W, vmax, p.is_localised, p.vel + (size_t)b * n, slice_outputs(p.out, b, H), wrec,
+                             p.use_warm != 0);
 }
 
 // Kernel 2: control QP + unpack + rollout + cost.
@@ -176,7 +180,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C == 2 ? 2 :
         // the raw path slice lands in the scratch region: it is dead before the first factorisation
         stage_path(c.W, p.paths + (size_t)b * 3 * H, H, p.use_tma, mbar, lane);
         const double offset = p.offsets ? p.offsets[b] : 0.0;
-        acmpc::control_instance<C>(c, c.W, p.vel + (size_t)b * n, offset, slice_outputs(p.out, b, H));
+        double* wrec = p.warm ? p.warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;
+        acmpc::control_instance<C>(c, c.W, p.vel + (size_t)b * n, offset, slice_outputs(p.out, b, H), wrec,
+                                   p.use_warm != 0);
         if (!p.persistent) break;
         uint32_t ticket = 0;
         if (lane == 0) ticket = atomicAdd(p.queue, 1u);
@@ -216,6 +222,8 @@ struct acmpc_handle {
     // device arena for the host entry point
     void* d_arena;
     size_t arena_bytes;
+    void* d_warm;            // warm-start records of the host entry point (keep_warm)
+    int warm_B;
     void* d_vel;             // speed-profile hand-over buffer of the device entry point (when v_ref is not requested)
     size_t vel_bytes;
     uint32_t* d_queue;       // ticket counter of the persistent warps (see KernelParams)
@@ -271,6 +279,16 @@ size_t smem_bytes_for(int H)   // dynamic shared memory per CTA
     }
 }
 
+size_t warm_bytes_for(int H)
+{
+    switch (stages_per_lane(H)) {
+        case 1: return sizeof(double) * acmpc::Layout<1>::kWarmDoubles;
+        case 2: return sizeof(double) * acmpc::Layout<2>::kWarmDoubles;
+        case 3: return sizeof(double) * acmpc::Layout<3>::kWarmDoubles;
+        default: return sizeof(double) * acmpc::Layout<4>::kWarmDoubles;
+    }
+}
+
 int tmem_cols_for(int H)
 {
     switch (stages_per_lane(H)) {
@@ -314,7 +332,8 @@ size_t speed_smem_bytes_for(int H)
 // Two launches on `stream`: the speed-profile kernel, then the control kernel.  `d_vel` [B,n] is the
 // hand-over buffer between them.
 int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offsets, const double* d_vmax,
-           int is_localised, const acmpc_outputs* d_out, double* d_vel, cudaStream_t stream)
+           int is_localised, const acmpc_outputs* d_out, double* d_vel, double* d_warm, int use_warm,
+           cudaStream_t stream)
 {
     KernelParams p;
     memset(&p, 0, sizeof(p));
@@ -322,6 +341,7 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     p.paths = d_paths, p.offsets = d_offsets, p.vmax = d_vmax;
     p.out = *d_out;
     p.vel = d_vel;
+    p.warm = d_warm, p.use_warm = (d_warm && use_warm) ? 1 : 0;
     p.B = B, p.is_localised = is_localised ? 1 : 0;
     const int H = h->cfg.horizon;
     // TMA bulk copies need 16-byte aligned ends and a size that is a multiple of 16
@@ -411,6 +431,7 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
     h->sm_count = prop.multiProcessorCount;
     h->d_queue = nullptr, h->queue_pos = 0;
     h->d_vel = nullptr, h->vel_bytes = 0;
+    h->d_warm = nullptr, h->warm_B = 0;
     h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
     {
         const char* e = getenv("ACMPC_PERSISTENT");
@@ -463,6 +484,7 @@ int32_t acmpc_destroy(acmpc_handle* h)
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->d_queue) cudaFree(h->d_queue);
     if (h->d_vel) cudaFree(h->d_vel);
+    if (h->d_warm) cudaFree(h->d_warm);
     if (h->ev) {
         for (int i = 0; i < 3 * kEventRing; ++i) cudaEventDestroy(h->ev[i]);
         delete[] h->ev;
@@ -474,11 +496,7 @@ int32_t acmpc_destroy(acmpc_handle* h)
 
 const char* acmpc_last_error(const acmpc_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
-int64_t acmpc_warm_stride(const acmpc_handle* h)
-{
-    (void)h;
-    return 0;   // warm-start records are not implemented in this ABI revision
-}
+int64_t acmpc_warm_stride(const acmpc_handle* h) { return h ? (int64_t)warm_bytes_for(h->cfg.horizon) : 0; }
 
 int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_paths, const double* d_offsets,
                                  const double* d_vmax, int32_t is_localised, void* d_warm, int32_t warm_valid,
@@ -489,8 +507,12 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
         h->err = "bad arguments";
         return ACMPC_ERR_INVALID;
     }
-    if (d_warm || warm_valid) {
-        h->err = "warm start is not implemented in this ABI revision";
+    if (warm_valid && !d_warm) {
+        h->err = "warm_valid without a warm-start buffer";
+        return ACMPC_ERR_INVALID;
+    }
+    if (d_warm && (reinterpret_cast<uintptr_t>(d_warm) & 7)) {
+        h->err = "warm-start buffer must be 8-byte aligned";
         return ACMPC_ERR_INVALID;
     }
     if (B == 0) return ACMPC_OK;
@@ -504,13 +526,15 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
                 cudaFree(h->d_vel);
             }
             h->d_vel = nullptr, h->vel_bytes = 0;
+    h->d_warm = nullptr, h->warm_B = 0;
     h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
             if (fail(h, cudaMalloc(&h->d_vel, need), "cudaMalloc(vel)")) return ACMPC_ERR_CUDA;
             h->vel_bytes = need;
         }
         d_vel = static_cast<double*>(h->d_vel);
     }
-    return launch(h, B, d_paths, d_offsets, d_vmax, is_localised, d_out, d_vel, static_cast<cudaStream_t>(stream));
+    return launch(h, B, d_paths, d_offsets, d_vmax, is_localised, d_out, d_vel, static_cast<double*>(d_warm),
+                  warm_valid, static_cast<cudaStream_t>(stream));
 }
 
 int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, const double* offsets,
@@ -522,12 +546,20 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
         h->err = "bad arguments";
         return ACMPC_ERR_INVALID;
     }
-    if (keep_warm) {
-        h->err = "warm start is not implemented in this ABI revision";
-        return ACMPC_ERR_INVALID;
-    }
     if (B == 0) return ACMPC_OK;
     if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    // keep_warm: the handle plays the reference's persistent solver objects -- one zero-initialised record
+    // per instance slot, dropped (cold restart) when the batch size changes or keep_warm is 0
+    if (!keep_warm || B != h->warm_B) {
+        if (h->d_warm) cudaFree(h->d_warm);
+        h->d_warm = nullptr, h->warm_B = 0;
+    }
+    if (keep_warm && !h->d_warm) {
+        const size_t wb = (size_t)B * warm_bytes_for(h->cfg.horizon);
+        if (fail(h, cudaMalloc(&h->d_warm, wb), "cudaMalloc(warm)")) return ACMPC_ERR_CUDA;
+        if (fail(h, cudaMemsetAsync(h->d_warm, 0, wb, h->stream), "cudaMemset(warm)")) return ACMPC_ERR_CUDA;
+        h->warm_B = B;
+    }
     const int H = h->cfg.horizon, n = H - 1;
     const size_t nb = (size_t)B;
     // arena layout (all 16-byte aligned): inputs then one slab per output field
@@ -571,7 +603,7 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
     int rc = launch(h, B, reinterpret_cast<const double*>(base + o_paths),
                     offsets ? reinterpret_cast<const double*>(base + o_off) : nullptr,
                     vmax ? reinterpret_cast<const double*>(base + o_vmax) : nullptr, is_localised, &d,
-                    reinterpret_cast<double*>(base + o_vr), s);
+                    reinterpret_cast<double*>(base + o_vr), static_cast<double*>(h->d_warm), 1, s);
     if (rc != ACMPC_OK) return rc;
 #define ACMPC_D2H(field, bytes)                                                                              \
     if (out->field &&                                                                                         \

@@ -85,8 +85,20 @@ enum : int {
     W_FIELDS = 15
 };
 
+// Warm-start record of one instance (the reference's three persistent OSQP objects, spatial_mpc.py:43-58:
+// speed-profile solver, localised speed-profile solver, control solver): header, then the SCALED iterates
+// exactly as OSQP keeps them between solves, one 32-lane row per (field, stage-in-lane).
+enum : int {
+    WR_RHO = 0,       // 3: rho of slot 0 (speed), 1 (localised speed), 2 (control)
+    WR_VALID = 3,     // 3: 1.0 once the slot holds a solve (0.0 = the object does not exist yet: cold setup)
+    WR_HEADER = 8,
+    WR_SPEED_FIELDS = 5,    // x za zb ya yb
+    WR_CTRL_FIELDS = 21     // x[5] zb[5] yb[5] ye[3] ze[3]
+};
+
 template <int C>
 struct Layout {
+    static constexpr int kWarmDoubles = WR_HEADER + (2 * WR_SPEED_FIELDS + WR_CTRL_FIELDS) * C * 32;
     static constexpr int kScratch = ((W_FIELDS * C > kLevels * 9) ? W_FIELDS * C : kLevels * 9) * 32;
     static constexpr int kDoubles = K_FIELDS * C * 32 + kScratch;   // shared memory per warp, control phase
     static constexpr int kSpeedDoubles = (2 * C * 32 > 3 * 32 * C) ? 2 * C * 32 : 3 * 32 * C;   // speed phase: raw path / LDL work
@@ -692,16 +704,26 @@ struct SpeedQP {
     }
 
     // osqp_solve, cold start.  Result (unscaled v) -> vout.
-    AC_MEM void solve(SolveInfo& info, VD (&vout)[C])
+    // `warm` = this instance's warm-start record or nullptr; `slot` 0 / 1 = the (un)localised solver object.
+    // `use_warm`: start from the record when its slot is valid (OSQP warm_start = True after update()).
+    AC_MEM void solve(SolveInfo& info, VD (&vout)[C], double* warm, int slot, bool use_warm)
     {
         const acmpc_config& g = *c.cfg;
         const double alpha = g.alpha, sigma = g.sigma;
-        R.set(clampu(g.rho, kRhoMin, kRhoMax));
+        double* wrow = warm ? warm + WR_HEADER + slot * WR_SPEED_FIELDS * C * 32 : nullptr;
+        const bool have = warm && use_warm && warm[WR_VALID + slot] != 0.0;
+        R.set(have ? warm[WR_RHO + slot] : clampu(g.rho, kRhoMin, kRhoMax));
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
             x[j] = za[j] = zb[j] = ya[j] = yb[j] = VD(0.0);
             dx[j] = dya[j] = dyb[j] = VD(0.0);
+            if (have) {
+                x[j] = ld_lane(wrow + (0 * C + j) * 32), za[j] = ld_lane(wrow + (1 * C + j) * 32);
+                zb[j] = ld_lane(wrow + (2 * C + j) * 32), ya[j] = ld_lane(wrow + (3 * C + j) * 32);
+                yb[j] = ld_lane(wrow + (4 * C + j) * 32);
+            }
         }
+        warp_sync();
         factor();
         Norms N;
         int status = 0, iter = 0, updates = 0;
@@ -754,6 +776,19 @@ struct SpeedQP {
             vout[j] = x[j] / di[j];
         }
         info.obj_val = final_obj(status, wsum(obj) * cinv);
+        if (warm) {
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                st_lane(wrow + (0 * C + j) * 32, x[j]), st_lane(wrow + (1 * C + j) * 32, za[j]);
+                st_lane(wrow + (2 * C + j) * 32, zb[j]), st_lane(wrow + (3 * C + j) * 32, ya[j]);
+                st_lane(wrow + (4 * C + j) * 32, yb[j]);
+            }
+            AC_LANE0
+            {
+                warm[WR_RHO + slot] = R.rho;
+                warm[WR_VALID + slot] = 1.0;
+            }
+        }
     }
 };
 
@@ -1383,15 +1418,29 @@ struct ControlQP {
         return 0;
     }
 
-    AC_MEM void solve(SolveInfo& info)
+    AC_MEM void solve(SolveInfo& info, double* warm, bool use_warm)
     {
         const acmpc_config& g = *c.cfg;
-        R.set(clampu(g.rho, kRhoMin, kRhoMax));
+        double* wrow = warm ? warm + WR_HEADER + 2 * WR_SPEED_FIELDS * C * 32 : nullptr;
+        const bool have = warm && use_warm && warm[WR_VALID + 2] != 0.0;
+        R.set(have ? warm[WR_RHO + 2] : clampu(g.rho, kRhoMin, kRhoMax));
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
             for (int e = 0; e < 5; ++e) x[j][e] = zb[j][e] = yb[j][e] = dx[j][e] = dyb[j][e] = VD(0.0);
             for (int r = 0; r < 3; ++r) ye[j][r] = ze[j][r] = dye[j][r] = VD(0.0);
+            if (have) {
+                for (int e = 0; e < 5; ++e) {
+                    x[j][e] = ld_lane(wrow + ((0 + e) * C + j) * 32);
+                    zb[j][e] = ld_lane(wrow + ((5 + e) * C + j) * 32);
+                    yb[j][e] = ld_lane(wrow + ((10 + e) * C + j) * 32);
+                }
+                for (int r = 0; r < 3; ++r) {
+                    ye[j][r] = ld_lane(wrow + ((15 + r) * C + j) * 32);
+                    ze[j][r] = ld_lane(wrow + ((18 + r) * C + j) * 32);
+                }
+            }
         }
+        warp_sync();
         factor();
         Norms N;
         int status = 0, iter = 0, updates = 0;
@@ -1444,6 +1493,25 @@ struct ControlQP {
                 if (e >= 3) obj = obj + tm_ld1(c.tm, j * T_STRIDE + T_H + HC_Q + e - 3) * xe;
             }
         info.obj_val = final_obj(status, wsum(obj) * cinv);
+        if (warm) {
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                for (int e = 0; e < 5; ++e) {
+                    st_lane(wrow + ((0 + e) * C + j) * 32, x[j][e]);
+                    st_lane(wrow + ((5 + e) * C + j) * 32, zb[j][e]);
+                    st_lane(wrow + ((10 + e) * C + j) * 32, yb[j][e]);
+                }
+                for (int r = 0; r < 3; ++r) {
+                    st_lane(wrow + ((15 + r) * C + j) * 32, ye[j][r]);
+                    st_lane(wrow + ((18 + r) * C + j) * 32, ze[j][r]);
+                }
+            }
+            AC_LANE0
+            {
+                warm[WR_RHO + 2] = R.rho;
+                warm[WR_VALID + 2] = 1.0;
+            }
+        }
     }
 };
 
@@ -1462,7 +1530,7 @@ struct InstanceOut {
 // spatial_mpc.py:115-122); it is the hand-over to phase 2.
 template <int C>
 AC_DEV void speed_instance(const Ctx<C>& c, const double* raw_path, double v_max_live, int localised,
-                           double* vel_out, const InstanceOut& o)
+                           double* vel_out, const InstanceOut& o, double* warm = nullptr, bool use_warm = false)
 {
     const int n = c.n;
     PathRegs<C> path;
@@ -1472,7 +1540,7 @@ AC_DEV void speed_instance(const Ctx<C>& c, const double* raw_path, double v_max
     VD vel[C];
     SpeedQP<C> sq(c);
     sq.assemble_and_scale(path, v_max_live, localised);
-    sq.solve(si, vel);
+    sq.solve(si, vel, warm, localised ? 1 : 0, use_warm);
     AC_UNROLL
     for (int j = 0; j < C; ++j) {
         VI st = c.stage(j);
@@ -1502,7 +1570,7 @@ AC_DEV void speed_instance(const Ctx<C>& c, const double* raw_path, double v_max
 // staged raw path (cheaper than handing six rows per stage over); `vel_in` [n] is phase 1's profile.
 template <int C>
 AC_DEV void control_instance(const Ctx<C>& c, const double* raw_path, const double* vel_in, double offset,
-                             const InstanceOut& o)
+                             const InstanceOut& o, double* warm = nullptr, bool use_warm = false)
 {
     const int n = c.n, H = c.H;
     PathRegs<C> path;
@@ -1517,7 +1585,7 @@ AC_DEV void control_instance(const Ctx<C>& c, const double* raw_path, const doub
     }
     ControlQP<C> cq(c);
     cq.setup(path, vel, offset);
-    cq.solve(ci);
+    cq.solve(ci, warm, use_warm);
     // unpack (spatial_mpc.py:193-212) and roll out (dynamics.py:42-63)
     const double L = c.cfg->wheelbase;
     AC_UNROLL

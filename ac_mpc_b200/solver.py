@@ -115,8 +115,11 @@ class BatchedMPC:
         arrs["_keepalive"] = keep
         return arrs
 
-    def solve_host(self, paths, offsets=None, vmax=None, is_localised: bool = False, out=None, fields=None):
-        """HOST buffers in, HOST buffers out (acmpc_solve_batch_host): H2D + kernel + D2H + sync."""
+    def solve_host(self, paths, offsets=None, vmax=None, is_localised: bool = False, out=None, fields=None,
+                   keep_warm: bool = False):
+        """HOST buffers in, HOST buffers out (acmpc_solve_batch_host): H2D + kernels + D2H + sync.
+        keep_warm: consecutive calls with the same B behave like B persistent reference objects (OSQP warm
+        start + carried rho, spatial_mpc.py:43-58); False = cold start per call."""
         paths = np.ascontiguousarray(paths, dtype=np.float64)
         if paths.ndim != 3 or paths.shape[1:] != (self.H, 3):
             raise ValueError(f"paths must be (B, {self.H}, 3), got {paths.shape}")
@@ -135,7 +138,7 @@ class BatchedMPC:
         dp = C.POINTER(C.c_double)
         ptr = lambda a: a.ctypes.data_as(dp) if a is not None else None
         self._check(self._lib.acmpc_solve_batch_host(self._handle(), B, ptr(paths), ptr(offsets), ptr(vmax),
-                                                     int(bool(is_localised)), 0, C.byref(o)))
+                                                     int(bool(is_localised)), int(bool(keep_warm)), C.byref(o)))
         return out
 
     # -- device buffers -------------------------------------------------------------------------
@@ -175,9 +178,21 @@ class BatchedMPC:
             total = (total + nbytes + 255) // 256 * 256
         return views
 
-    def solve_device(self, paths, offsets=None, vmax=None, is_localised: bool = False, out=None, stream=None):
+    def warm_stride(self) -> int:
+        """Bytes of one instance's warm-start record."""
+        return int(self._lib.acmpc_warm_stride(self._handle()))
+
+    def alloc_warm(self, B: int):
+        """Zero-filled device buffer of B warm-start records ("no solver object yet")."""
+        import torch
+
+        return torch.zeros(B * self.warm_stride() // 8, dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def solve_device(self, paths, offsets=None, vmax=None, is_localised: bool = False, out=None, stream=None,
+                     warm=None, warm_valid: bool = True):
         """DEVICE tensors in/out (acmpc_solve_batch_device); asynchronous on `stream` (torch stream or
-        None = torch's current stream).  `out` = dict of CUDA tensors from alloc_device_outputs."""
+        None = torch's current stream).  `out` = dict of CUDA tensors from alloc_device_outputs.
+        `warm`: tensor from alloc_warm (read when warm_valid, always rewritten) or None = cold start."""
         import torch
 
         if not (paths.is_cuda and paths.dtype == torch.float64 and paths.is_contiguous()):
@@ -197,7 +212,8 @@ class BatchedMPC:
         s = torch.cuda.current_stream(paths.device) if stream is None else stream
         self._check(self._lib.acmpc_solve_batch_device(
             self._handle(), B, paths.data_ptr(), None if offsets is None else offsets.data_ptr(),
-            None if vmax is None else vmax.data_ptr(), int(bool(is_localised)), None, 0, C.byref(o),
+            None if vmax is None else vmax.data_ptr(), int(bool(is_localised)),
+            None if warm is None else warm.data_ptr(), int(bool(warm_valid and warm is not None)), C.byref(o),
             C.c_void_p(s.cuda_stream)))
         return out
 

@@ -103,7 +103,10 @@ int32_t acmpc_create(const acmpc_config *cfg, int32_t device, acmpc_handle **out
 int32_t acmpc_destroy(acmpc_handle *h);
 const char *acmpc_last_error(const acmpc_handle *h);
 
-/* bytes of one instance's packed warm-start record (scaled x,z,y + rho of both QPs) */
+/* bytes of one instance's warm-start record: the state the reference's three persistent OSQP objects keep
+ * between calls (spatial_mpc.py:43-58: speed-profile solver, localised speed-profile solver, control
+ * solver) -- scaled x, z, y, the adapted rho and an "object exists" flag each.  A zero-filled record means
+ * "no object yet": the first solve of a slot is a cold setup, exactly like the reference's first call. */
 int64_t acmpc_warm_stride(const acmpc_handle *h);
 
 /* One MPC step for B independent instances, everything resident on the device.
@@ -111,8 +114,10 @@ int64_t acmpc_warm_stride(const acmpc_handle *h);
  *   d_offsets [B] lateral offset (get_control arg 3) or NULL (= 0.0)
  *   d_vmax    [B] live speed_profile_constraints["v_max"] (controller.py:241-243) or NULL (= cfg.v_max)
  *   is_localised: get_control arg 2
- *   d_warm    NULL = cold start (x=z=y=0, rho=cfg.rho) ; else [B, acmpc_warm_stride] bytes, read
- *             when warm_valid != 0 and always rewritten (the reference's persistent OSQP objects)
+ *   d_warm    NULL = cold start (x=z=y=0, rho=cfg.rho) ; else [B, acmpc_warm_stride] bytes (8-byte aligned,
+ *             zero-filled by the caller before first use), read when warm_valid != 0 and always rewritten
+ *             (the reference's persistent OSQP objects: OSQP warm-starts x, y, z and keeps the adapted rho,
+ *             while update() re-equilibrates the new data)
  *   stream    cudaStream_t (NULL = default stream).  Asynchronous: no host sync inside (except when the
  *             internal speed-profile hand-over buffer has to grow: first call, or a larger B, with
  *             d_out->v_ref == NULL).  Calls on one handle must be stream-ordered with each other (the
@@ -123,9 +128,10 @@ int32_t acmpc_solve_batch_device(acmpc_handle *h, int32_t B, const double *d_pat
                                  int32_t is_localised, void *d_warm, int32_t warm_valid,
                                  const acmpc_outputs *d_out, void *stream);
 
-/* Same with HOST buffers: copies inputs to the device, runs the kernel, copies every non-NULL
- * output back and synchronises.  (Warm-start records stay on the device inside the handle when
- * keep_warm != 0: this is the B=1 path the drop-in SpatialMPC.get_control uses.) */
+/* Same with HOST buffers: copies inputs to the device, runs the kernels, copies every non-NULL
+ * output back and synchronises.  keep_warm != 0: instance slot b of consecutive calls with the same B is one
+ * persistent solver object (records live on the device inside the handle; a different B or a call with
+ * keep_warm == 0 drops them) -- the B = 1 path the drop-in SpatialMPC.get_control uses. */
 int32_t acmpc_solve_batch_host(acmpc_handle *h, int32_t B, const double *paths,
                                const double *offsets, const double *vmax, int32_t is_localised,
                                int32_t keep_warm, const acmpc_outputs *out);

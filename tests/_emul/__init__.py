@@ -24,17 +24,22 @@ def lib():
         _lib = C.CDLL(_SO)
         dp = C.POINTER(C.c_double)
         _lib.acmpc_emul_solve_batch.argtypes = [C.POINTER(port.Config), C.c_int, dp, dp, dp, C.c_int,
-                                                C.POINTER(port.Outputs)]
+                                                C.POINTER(port.Outputs), dp, C.c_int]
     return _lib
 
 
-def solve_batch(cfg, paths, offsets=None, vmax=None, is_localised=False):
+def warm_buffer(cfg, B):
+    """Zeroed warm-start records for B instances (the emulation's counterpart of acmpc_warm_stride)."""
+    return np.zeros((B, lib().acmpc_emul_warm_doubles(int(cfg.horizon))), dtype=np.float64)
+
+
+def solve_batch(cfg, paths, offsets=None, vmax=None, is_localised=False, warm=None, use_warm=True):
     paths = np.ascontiguousarray(paths, dtype=np.float64)
     B, H, _ = paths.shape
     offsets = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.float64)
     vmax = None if vmax is None else np.ascontiguousarray(vmax, dtype=np.float64)
     arrs, o = port.alloc_outputs(B, H)
     rc = lib().acmpc_emul_solve_batch(C.byref(cfg), B, port._dptr(paths), port._dptr(offsets), port._dptr(vmax),
-                                      int(bool(is_localised)), C.byref(o))
+                                      int(bool(is_localised)), C.byref(o), port._dptr(warm), int(bool(use_warm)))
     assert rc == 0
     return arrs

@@ -14,7 +14,7 @@ namespace {
 
 template <int C>
 void run(const acmpc_config* cfg, int B, const double* paths, const double* offsets, const double* vmax,
-         int is_localised, const acmpc_outputs* out)
+         int is_localised, const acmpc_outputs* out, double* warm, int use_warm)
 {
     const int H = cfg->horizon, n = H - 1;
     const size_t nd = (size_t)acmpc::smem_doubles<C>();
@@ -45,10 +45,11 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
         o.rho_updates = out->rho_updates ? out->rho_updates + (size_t)b * 2 : nullptr;
         o.waypoints = out->waypoints ? out->waypoints + (size_t)b * 7 * n : nullptr;
         // the two phases are two kernels in the product; the hand-over is the speed profile
-        acmpc::speed_instance<C>(c, raw, vmax ? vmax[b] : cfg->v_max, is_localised, vel, o);
+        double* wrec = warm ? warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;
+        acmpc::speed_instance<C>(c, raw, vmax ? vmax[b] : cfg->v_max, is_localised, vel, o, wrec, use_warm != 0);
         memset(smem, 0xff, sizeof(double) * nd);
         memcpy(raw, paths + (size_t)b * 3 * H, sizeof(double) * 3 * (size_t)H);
-        acmpc::control_instance<C>(c, raw, vel, offsets ? offsets[b] : 0.0, o);
+        acmpc::control_instance<C>(c, raw, vel, offsets ? offsets[b] : 0.0, o, wrec, use_warm != 0);
     }
     free(smem);
     free(tmem);
@@ -57,17 +58,28 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
 
 }  // namespace
 
+extern "C" int acmpc_emul_warm_doubles(int H)
+{
+    switch ((H + 31) / 32) {
+        case 1: return acmpc::Layout<1>::kWarmDoubles;
+        case 2: return acmpc::Layout<2>::kWarmDoubles;
+        case 3: return acmpc::Layout<3>::kWarmDoubles;
+        default: return acmpc::Layout<4>::kWarmDoubles;
+    }
+}
+
+// `warm`: NULL or [B, acmpc_emul_warm_doubles(H)] doubles (zero-initialised by the caller before first use)
 extern "C" int acmpc_emul_solve_batch(const acmpc_config* cfg, int B, const double* paths,
                                       const double* offsets, const double* vmax, int is_localised,
-                                      const acmpc_outputs* out)
+                                      const acmpc_outputs* out, double* warm, int use_warm)
 {
     const int H = cfg->horizon;
     if (H < ACMPC_MIN_HORIZON || H > ACMPC_MAX_HORIZON) return ACMPC_ERR_INVALID;
     switch ((H + 31) / 32) {
-        case 1: run<1>(cfg, B, paths, offsets, vmax, is_localised, out); break;
-        case 2: run<2>(cfg, B, paths, offsets, vmax, is_localised, out); break;
-        case 3: run<3>(cfg, B, paths, offsets, vmax, is_localised, out); break;
-        default: run<4>(cfg, B, paths, offsets, vmax, is_localised, out); break;
+        case 1: run<1>(cfg, B, paths, offsets, vmax, is_localised, out, warm, use_warm); break;
+        case 2: run<2>(cfg, B, paths, offsets, vmax, is_localised, out, warm, use_warm); break;
+        case 3: run<3>(cfg, B, paths, offsets, vmax, is_localised, out, warm, use_warm); break;
+        default: run<4>(cfg, B, paths, offsets, vmax, is_localised, out, warm, use_warm); break;
     }
     return 0;
 }

@@ -239,3 +239,65 @@ def test_baseline_config5_all_tracks_shards(track):
     got = {k: np.concatenate([p[k] for p in parts]) for k in parts[0] if not k.startswith("_")}
     want = port.solve_batch(port.default_config(**kw), paths, None, vmax, nthreads=16)
     _assert_equals_oracle(got, want, fields=("controls", "cost"))
+
+
+def test_warm_start_object_reuse_matches_reference_golden():
+    """The reference test reuses ONE SpatialMPC for its 28 fixture paths (warm-started OSQP objects, carried
+    rho): golden group fixture_warm, through the drop-in object API and the host entry point (keep_warm)."""
+    import _golden
+    from ac_mpc_b200.control import build_mpc
+
+    G = _golden.load()
+    g, paths = G["fixture_warm"], G["fixture_cold"]["paths"]
+    veh = type("V", (), {"vehicle_data": type("D", (), {"wheelbase": 2.65, "width": 1.99})(),
+                         "max_steering_angle": lambda self: 0.3})()
+    cfg = {"horizon": 100, "step_cost": _golden.FIXTURE_CONFIG["step_cost"], "r_term": [1e-2, 10.0],
+           "final_cost": [1.0, 0.0, 0.1],
+           "speed_profile_constraints": {k: _golden.FIXTURE_CONFIG[k] for k in ("v_min", "v_max", "a_min", "a_max", "ay_max", "ki_min", "end_velocity")}}
+    mpc = build_mpc(cfg, veh)
+    for b in range(paths.shape[0]):
+        mpc.get_control(paths[b])
+        assert mpc.last_info["iters"] == g["iters"][b].tolist(), b
+        assert mpc.last_info["rho_updates"] == g["rho_updates"][b].tolist(), b
+        if g["status"][b] == 1:
+            np.testing.assert_allclose(mpc.projected_control, g["controls"][b], rtol=0, atol=TOL)
+            np.testing.assert_allclose(mpc.current_prediction, g["prediction"][b], rtol=0, atol=TOL)
+
+
+def test_warm_start_closed_loop_replay_matches_oracle_objects():
+    """BASELINE configs[2] "closed-loop replay": instances advance along the Nordschleife centreline step by step,
+    warm-started from their previous solve (device entry point, one record per instance), alternating
+    is_localised (two separate speed-solver objects); a sample of the records is checked against oracle
+    objects driven through the same sequence, and warm_valid=0 must reproduce the cold solve."""
+    import _golden
+    import torch
+
+    kw = _golden.racing_kwargs("nordschleife")
+    cl = tracks.synthetic_centreline("nordschleife")
+    B, steps = 2048, 4
+    start = np.random.default_rng(9).integers(0, cl.shape[0], B)
+    mpc = _solver(**kw)
+    warm = mpc.alloc_warm(B)
+    assert warm.numel() * 8 == B * mpc.warm_stride()
+    sample = np.random.default_rng(1).choice(B, 24, replace=False)
+    objs = {int(b): port.PortMPC(port.default_config(**kw)) for b in sample}
+    packed, views = mpc.alloc_device_outputs(B, ["controls", "status", "iters", "rho_updates", "cost"])
+    for t in range(steps):
+        paths = tracks.make_instances(cl, (start + 30 * t) % cl.shape[0], 50)
+        loc = bool(t % 2)
+        mpc.solve_device(torch.from_numpy(paths).cuda(), None, None, loc, out=views, warm=warm)
+        torch.cuda.synchronize()
+        got = {k: v.cpu().numpy() for k, v in views.items()}
+        for b, obj in objs.items():
+            want = obj.step(paths[b], 0.0, None, loc, warm=True)
+            assert got["iters"][b].tolist() == want["iters"].tolist(), (t, b)
+            assert got["rho_updates"][b].tolist() == want["rho_updates"].tolist(), (t, b)
+            assert got["status"][b] == want["status"]
+            np.testing.assert_allclose(got["controls"][b], want["controls"], rtol=0, atol=TOL)
+    # warm starts change the iteration counts of most instances after the first step
+    cold = mpc.solve_host(paths, None, None, loc, fields=["controls", "iters"])
+    assert (got["iters"] != cold["iters"]).any()
+    mpc.solve_device(torch.from_numpy(paths).cuda(), None, None, loc, out=views, warm=warm, warm_valid=False)
+    torch.cuda.synchronize()
+    assert np.array_equal(views["iters"].cpu().numpy(), cold["iters"])
+    assert np.array_equal(views["controls"].cpu().numpy(), cold["controls"])
