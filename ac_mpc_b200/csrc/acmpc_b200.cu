@@ -218,7 +218,8 @@ struct acmpc_handle {
     int sm_count;
     int ctas_per_sm;
     std::string err;
-    cudaStream_t stream;     // owned, used by the host entry point
+    cudaStream_t stream;     // owned, used by the host entry point (= streams[0])
+    cudaStream_t streams[4]; // the host entry point pipelines large batches as up to 4 chunks
     // device arena for the host entry point
     void* d_arena;
     size_t arena_bytes;
@@ -226,8 +227,8 @@ struct acmpc_handle {
     int warm_B;
     void* d_vel;             // speed-profile hand-over buffer of the device entry point (when v_ref is not requested)
     size_t vel_bytes;
-    uint32_t* d_queue;       // ticket counter of the persistent warps (see KernelParams)
-    uint32_t queue_pos;      // its value once every launch issued so far has completed
+    uint32_t* d_queue;       // 4 ticket counters of the persistent warps (see KernelParams), one per chunk stream
+    uint32_t queue_pos[4];   // their values once every launch issued so far has completed
     int profiling;           // record events around the two kernels (acmpc_set_profiling)
     cudaEvent_t* ev;         // 3 * kEventRing events
     int ev_head, ev_count;
@@ -333,7 +334,7 @@ size_t speed_smem_bytes_for(int H)
 // hand-over buffer between them.
 int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offsets, const double* d_vmax,
            int is_localised, const acmpc_outputs* d_out, double* d_vel, double* d_warm, int use_warm,
-           cudaStream_t stream)
+           cudaStream_t stream, int qi = 0)
 {
     KernelParams p;
     memset(&p, 0, sizeof(p));
@@ -355,8 +356,8 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     p.persistent = h->persistent;
     if (p.persistent && ctas > resident) ctas = resident;
     if (getenv("ACMPC_DEBUG")) fprintf(stderr, "acmpc launch: B=%d ctas=%d ctas_per_sm=%d sms=%d smem=%zu\n", B, ctas, h->ctas_per_sm, h->sm_count, smem);
-    p.queue = h->d_queue, p.queue_base = h->queue_pos, p.warps_launched = (uint32_t)(ctas * kWarpsPerCta);
-    if (p.persistent) h->queue_pos += (uint32_t)B;   // every solved instance draws one ticket
+    p.queue = h->d_queue + qi, p.queue_base = h->queue_pos[qi], p.warps_launched = (uint32_t)(ctas * kWarpsPerCta);
+    if (p.persistent) h->queue_pos[qi] += (uint32_t)B;   // every solved instance draws one ticket
     cudaEvent_t* ev = nullptr;
     if (h->profiling && h->ev) {
         ev = h->ev + 3 * h->ev_head;
@@ -373,7 +374,7 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     if (fail(h, cudaLaunchKernel(kernel_for(H), dim3(ctas), dim3(32 * kWarpsPerCta), args, smem, stream), "kernel launch"))
         return ACMPC_ERR_CUDA;
     if (ev) cudaEventRecord(ev[2], stream);
-    h->last_launches = 2, h->last_smem = (int)smem, h->last_threads = 32 * kWarpsPerCta, h->last_ipc = kWarpsPerCta;
+    h->last_launches += 2, h->last_smem = (int)smem, h->last_threads = 32 * kWarpsPerCta, h->last_ipc = kWarpsPerCta;
     if (fail(h, cudaGetLastError(), "kernel launch")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
 }
@@ -429,7 +430,8 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
         return ACMPC_ERR_NO_DEVICE;
     }
     h->sm_count = prop.multiProcessorCount;
-    h->d_queue = nullptr, h->queue_pos = 0;
+    h->d_queue = nullptr;
+    for (int k = 0; k < 4; ++k) h->queue_pos[k] = 0, h->streams[k] = nullptr;
     h->d_vel = nullptr, h->vel_bytes = 0;
     h->d_warm = nullptr, h->warm_B = 0;
     h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
@@ -447,20 +449,24 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
         fail(h, cudaFuncSetAttribute(kernel_for(cfg->horizon), cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared),
              "cudaFuncSetAttribute(carveout)") ||
-        fail(h, cudaMalloc(&h->d_queue, sizeof(uint32_t)), "cudaMalloc(queue)") ||
-        fail(h, cudaMemset(h->d_queue, 0, sizeof(uint32_t)), "cudaMemset(queue)") ||
-        fail(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        fail(h, cudaMalloc(&h->d_queue, 4 * sizeof(uint32_t)), "cudaMalloc(queue)") ||
+        fail(h, cudaMemset(h->d_queue, 0, 4 * sizeof(uint32_t)), "cudaMemset(queue)") ||
+        fail(h, cudaStreamCreateWithFlags(&h->streams[0], cudaStreamNonBlocking), "cudaStreamCreate") ||
+        fail(h, cudaStreamCreateWithFlags(&h->streams[1], cudaStreamNonBlocking), "cudaStreamCreate") ||
+        fail(h, cudaStreamCreateWithFlags(&h->streams[2], cudaStreamNonBlocking), "cudaStreamCreate") ||
+        fail(h, cudaStreamCreateWithFlags(&h->streams[3], cudaStreamNonBlocking), "cudaStreamCreate")) {
         if (h->d_queue) cudaFree(h->d_queue);
         delete h;
         return ACMPC_ERR_CUDA;
     }
+    h->stream = h->streams[0];
     // CTAs resident per SM = min over shared memory, registers and tensor memory (512 columns per SM).
     // (cudaOccupancyMaxActiveBlocksPerMultiprocessor assumes the default carve-out and under-reports.)
     {
         cudaFuncAttributes fa;
         if (fail(h, cudaFuncGetAttributes(&fa, kernel_for(cfg->horizon)), "cudaFuncGetAttributes")) {
             cudaFree(h->d_queue);
-            cudaStreamDestroy(h->stream);
+            for (int k = 0; k < 4; ++k) cudaStreamDestroy(h->streams[k]);
             delete h;
             return ACMPC_ERR_CUDA;
         }
@@ -489,7 +495,8 @@ int32_t acmpc_destroy(acmpc_handle* h)
         for (int i = 0; i < 3 * kEventRing; ++i) cudaEventDestroy(h->ev[i]);
         delete[] h->ev;
     }
-    cudaStreamDestroy(h->stream);
+    for (int k = 0; k < 4; ++k)
+        if (h->streams[k]) cudaStreamDestroy(h->streams[k]);
     delete h;
     return ACMPC_OK;
 }
@@ -517,6 +524,7 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
     }
     if (B == 0) return ACMPC_OK;
     if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    h->last_launches = 0;
     double* d_vel = d_out->v_ref;
     if (!d_vel) {   // the caller did not ask for v_ref: hand over through a scratch buffer owned by the handle
         const size_t need = (size_t)B * (h->cfg.horizon - 1) * sizeof(double);
@@ -578,52 +586,72 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
         h->arena_bytes = off;
     }
     char* base = static_cast<char*>(h->d_arena);
-    cudaStream_t s = h->stream;
-    if (fail(h, cudaMemcpyAsync(base + o_paths, paths, nb * 3 * H * 8, cudaMemcpyHostToDevice, s), "H2D paths"))
+    // Large batches go through as up to 4 chunks on 4 streams (own ticket queue each), so that the H2D copy of
+    // one chunk and the D2H copy of another overlap the kernels of a third.  (Async only from pinned host memory.)
+    const int chunks = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
+    const int per = ((B + chunks - 1) / chunks + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
+    const size_t wstride = warm_bytes_for(H);
+    h->last_launches = 0;
+    if (h->d_warm && chunks > 1 &&
+        fail(h, cudaStreamSynchronize(h->streams[0]), "cudaStreamSynchronize"))   // the zero-fill of new records
         return ACMPC_ERR_CUDA;
-    if (offsets && fail(h, cudaMemcpyAsync(base + o_off, offsets, nb * 8, cudaMemcpyHostToDevice, s), "H2D offsets"))
+    for (int k = 0; k < chunks; ++k) {
+        const int c0 = k * per;
+        const int cb = (c0 + per <= B) ? per : B - c0;
+        if (cb <= 0) break;
+        cudaStream_t s = h->streams[k];
+        const size_t z = (size_t)c0, nbk = (size_t)cb;
+        if (fail(h, cudaMemcpyAsync(base + o_paths + z * 3 * H * 8, paths + z * 3 * H, nbk * 3 * H * 8,
+                                    cudaMemcpyHostToDevice, s), "H2D paths"))
+            return ACMPC_ERR_CUDA;
+        if (offsets && fail(h, cudaMemcpyAsync(base + o_off + z * 8, offsets + z, nbk * 8, cudaMemcpyHostToDevice, s),
+                            "H2D offsets"))
+            return ACMPC_ERR_CUDA;
+        if (vmax && fail(h, cudaMemcpyAsync(base + o_vmax + z * 8, vmax + z, nbk * 8, cudaMemcpyHostToDevice, s),
+                         "H2D vmax"))
+            return ACMPC_ERR_CUDA;
+        acmpc_outputs d;
+        memset(&d, 0, sizeof(d));
+        if (out->controls) d.controls = reinterpret_cast<double*>(base + o_ctrl) + z * 2 * n;
+        if (out->prediction) d.prediction = reinterpret_cast<double*>(base + o_pred) + z * 2 * n;
+        if (out->cum_time) d.cum_time = reinterpret_cast<double*>(base + o_ct) + z * n;
+        if (out->states) d.states = reinterpret_cast<double*>(base + o_st) + z * 3 * H;
+        if (out->v_ref) d.v_ref = reinterpret_cast<double*>(base + o_vr) + z * n;
+        if (out->cost) d.cost = reinterpret_cast<double*>(base + o_cost) + z;
+        if (out->pri_res) d.pri_res = reinterpret_cast<double*>(base + o_pr) + z;
+        if (out->dua_res) d.dua_res = reinterpret_cast<double*>(base + o_dr) + z;
+        if (out->status) d.status = reinterpret_cast<int32_t*>(base + o_stat) + z;
+        if (out->status_speed) d.status_speed = reinterpret_cast<int32_t*>(base + o_ss) + z;
+        if (out->iters) d.iters = reinterpret_cast<int32_t*>(base + o_it) + z * 2;
+        if (out->rho_updates) d.rho_updates = reinterpret_cast<int32_t*>(base + o_ru) + z * 2;
+        if (out->waypoints) d.waypoints = reinterpret_cast<double*>(base + o_wp) + z * 7 * n;
+        int rc = launch(h, cb, reinterpret_cast<const double*>(base + o_paths) + z * 3 * H,
+                        offsets ? reinterpret_cast<const double*>(base + o_off) + z : nullptr,
+                        vmax ? reinterpret_cast<const double*>(base + o_vmax) + z : nullptr, is_localised, &d,
+                        reinterpret_cast<double*>(base + o_vr) + z * n,
+                        h->d_warm ? reinterpret_cast<double*>(static_cast<char*>(h->d_warm) + z * wstride) : nullptr, 1, s, k);
+        if (rc != ACMPC_OK) return rc;
+#define ACMPC_D2H(field, per_inst, type)                                                                        \
+    if (out->field && fail(h, cudaMemcpyAsync(out->field + z * (per_inst), d.field, nbk * (per_inst) * sizeof(type), \
+                                              cudaMemcpyDeviceToHost, s), "D2H " #field))                        \
         return ACMPC_ERR_CUDA;
-    if (vmax && fail(h, cudaMemcpyAsync(base + o_vmax, vmax, nb * 8, cudaMemcpyHostToDevice, s), "H2D vmax"))
-        return ACMPC_ERR_CUDA;
-    acmpc_outputs d;
-    memset(&d, 0, sizeof(d));
-    if (out->controls) d.controls = reinterpret_cast<double*>(base + o_ctrl);
-    if (out->prediction) d.prediction = reinterpret_cast<double*>(base + o_pred);
-    if (out->cum_time) d.cum_time = reinterpret_cast<double*>(base + o_ct);
-    if (out->states) d.states = reinterpret_cast<double*>(base + o_st);
-    if (out->v_ref) d.v_ref = reinterpret_cast<double*>(base + o_vr);
-    if (out->cost) d.cost = reinterpret_cast<double*>(base + o_cost);
-    if (out->pri_res) d.pri_res = reinterpret_cast<double*>(base + o_pr);
-    if (out->dua_res) d.dua_res = reinterpret_cast<double*>(base + o_dr);
-    if (out->status) d.status = reinterpret_cast<int32_t*>(base + o_stat);
-    if (out->status_speed) d.status_speed = reinterpret_cast<int32_t*>(base + o_ss);
-    if (out->iters) d.iters = reinterpret_cast<int32_t*>(base + o_it);
-    if (out->rho_updates) d.rho_updates = reinterpret_cast<int32_t*>(base + o_ru);
-    if (out->waypoints) d.waypoints = reinterpret_cast<double*>(base + o_wp);
-    int rc = launch(h, B, reinterpret_cast<const double*>(base + o_paths),
-                    offsets ? reinterpret_cast<const double*>(base + o_off) : nullptr,
-                    vmax ? reinterpret_cast<const double*>(base + o_vmax) : nullptr, is_localised, &d,
-                    reinterpret_cast<double*>(base + o_vr), static_cast<double*>(h->d_warm), 1, s);
-    if (rc != ACMPC_OK) return rc;
-#define ACMPC_D2H(field, bytes)                                                                              \
-    if (out->field &&                                                                                         \
-        fail(h, cudaMemcpyAsync(out->field, d.field, (bytes), cudaMemcpyDeviceToHost, s), "D2H " #field))     \
-        return ACMPC_ERR_CUDA;
-    ACMPC_D2H(controls, nb * 2 * n * 8)
-    ACMPC_D2H(prediction, nb * 2 * n * 8)
-    ACMPC_D2H(cum_time, nb * n * 8)
-    ACMPC_D2H(states, nb * 3 * H * 8)
-    ACMPC_D2H(v_ref, nb * n * 8)
-    ACMPC_D2H(cost, nb * 8)
-    ACMPC_D2H(pri_res, nb * 8)
-    ACMPC_D2H(dua_res, nb * 8)
-    ACMPC_D2H(status, nb * 4)
-    ACMPC_D2H(status_speed, nb * 4)
-    ACMPC_D2H(iters, nb * 8)
-    ACMPC_D2H(rho_updates, nb * 8)
-    ACMPC_D2H(waypoints, nb * 7 * n * 8)
+        ACMPC_D2H(controls, 2 * n, double)
+        ACMPC_D2H(prediction, 2 * n, double)
+        ACMPC_D2H(cum_time, n, double)
+        ACMPC_D2H(states, 3 * H, double)
+        ACMPC_D2H(v_ref, n, double)
+        ACMPC_D2H(cost, 1, double)
+        ACMPC_D2H(pri_res, 1, double)
+        ACMPC_D2H(dua_res, 1, double)
+        ACMPC_D2H(status, 1, int32_t)
+        ACMPC_D2H(status_speed, 1, int32_t)
+        ACMPC_D2H(iters, 2, int32_t)
+        ACMPC_D2H(rho_updates, 2, int32_t)
+        ACMPC_D2H(waypoints, 7 * n, double)
 #undef ACMPC_D2H
-    if (fail(h, cudaStreamSynchronize(s), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
+    }
+    for (int k = 0; k < chunks; ++k)
+        if (fail(h, cudaStreamSynchronize(h->streams[k]), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
 }
 
