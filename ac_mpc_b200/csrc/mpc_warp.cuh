@@ -662,7 +662,8 @@ struct SpeedQP {
         return 0;
     }
 
-    // one ADMM iteration (osqp_solve loop body)
+    // one ADMM iteration (osqp_solve loop body); KEEP: also record delta_x / delta_y for the certificates
+    template <bool KEEP>
     AC_MEM void iterate(const double alpha, const double sigma)
     {
         VD r[C], xt[C], xn[C], t[C], tp[C];
@@ -686,7 +687,7 @@ struct SpeedQP {
                 VD dy = rho_a[j] * (zh - zn);
                 za[j] = zn;
                 ya[j] = ya[j] + dy;
-                dya[j] = dy;
+                if (KEEP) dya[j] = dy;
             }
             {
                 VD zt = ss[j] * xt[j];
@@ -695,10 +696,10 @@ struct SpeedQP {
                 VD dy = rho_b[j] * (zh - zn);
                 zb[j] = zn;
                 yb[j] = yb[j] + dy;
-                dyb[j] = dy;
+                if (KEEP) dyb[j] = dy;
             }
             VD xnew = VD(alpha) * xt[j] + VD(1.0 - alpha) * x[j];
-            dx[j] = xnew - x[j];
+            if (KEEP) dx[j] = xnew - x[j];
             x[j] = xnew;
         }
     }
@@ -729,29 +730,26 @@ struct SpeedQP {
         int status = 0, iter = 0, updates = 0;
         // osqp_solve's order: iterate -> exact check (every check_termination iterations) -> adaptive rho;
         // at the iteration limit the exact check if it has not just run, then the 10x "inaccurate" one.
-        // `pass` 0 is an ADMM iteration, passes 1 and 2 are those two extra checks: check() has ONE call site.
-        int pass = 0;
+        // Iterations followed by a check / rho estimate are the KEEP instantiation and the check sits in the
+        // same block, so the delta vectors of the certificates never live across the loop; everything in the
+        // block is straight-line code (a loop over "phases" here once let LICM hoist rho_estimate's
+        // divisions into every iteration).
         bool checked = false, adapt = false, last = false;
         // countdowns instead of iter % interval (a runtime integer division per test)
         int to_check = g.check_termination > 0 ? g.check_termination : -1;
         int to_adapt = (g.adaptive_rho && g.adaptive_rho_interval > 0) ? g.adaptive_rho_interval : -1;
         for (;;) {
-            if (pass == 0) {
-                ++iter;
-                checked = (--to_check == 0);
-                if (checked) to_check = g.check_termination;
-                adapt = (--to_adapt == 0);
-                if (adapt) to_adapt = g.adaptive_rho_interval;
-                last = iter >= g.max_iter;
-                iterate(alpha, sigma);
-                if (checked || adapt || last) compute_norms(N);
-            }
-            if (pass > 0 || checked) {
-                status = check(N, pass == 2);
-                if (uni(status != 0)) break;
-            }
-            if (pass == 0) {
-                if (adapt) {
+            ++iter;
+            checked = (--to_check == 0);
+            if (checked) to_check = g.check_termination;
+            adapt = (--to_adapt == 0);
+            if (adapt) to_adapt = g.adaptive_rho_interval;
+            last = iter >= g.max_iter;
+            if (checked || adapt || last) {
+                iterate<true>(alpha, sigma);
+                compute_norms(N);
+                if (checked) status = check(N, 0);
+                if (uni(status == 0) && adapt) {
                     double rn = rho_estimate(N, R.rho);
                     if (uni(rn > R.rho * g.adaptive_rho_tolerance || rn < R.rho / g.adaptive_rho_tolerance)) {
                         R.set(rn);
@@ -759,12 +757,14 @@ struct SpeedQP {
                         factor();
                     }
                 }
-                if (last) pass = checked ? 2 : 1;
-            } else if (pass == 1) {
-                pass = 2;
+                if (uni(status == 0) && last) {
+                    if (!checked) status = check(N, 0);
+                    if (uni(status == 0)) status = check(N, 1);
+                    if (uni(status == 0)) status = ACMPC_MAX_ITER_REACHED;
+                }
+                if (uni(status != 0)) break;
             } else {
-                status = ACMPC_MAX_ITER_REACHED;
-                break;
+                iterate<false>(alpha, sigma);
             }
         }
         info.status = status, info.iter = iter, info.rho_updates = updates;
@@ -1199,16 +1199,25 @@ struct ControlQP {
     }
 
     // One ADMM iteration (osqp_solve loop body): rhs, reduced solve, recover inputs, relax, project, duals.
-    AC_MEM void iterate(bool keep_delta)
+    // FIRST: the first iteration of a solve reads the z of the equality rows from the start state (`ze`: zero on a
+    // cold start, the previous problem's right-hand side on a warm start); from then on that z IS the scaled
+    // right-hand side b (projection onto [b, b]), so the hot instantiation carries no ze registers.
+    // KEEP: also record delta_x / delta_y for the infeasibility certificates.  Only the iterations that are
+    // followed by a termination check are KEEP instantiations, and the check sits in the same block of
+    // solve(), so the 13 delta values per stage never live across the loop.
+    template <bool FIRST, bool KEEP>
+    AC_MEM void iterate()
     {
         const double sigma = c.cfg->sigma, alpha = c.cfg->alpha, re = R.rho_eq;
         VD t[C][3], tn[C][3], ru[C][2], r[C][3], xt[C][3], Aj[C][6];
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            VD F[16], G[16], Q[2];
+            VD F[16], G[16], Q[8];   // Q: q[2] be[3] lb[0..2]
             c.tld(T_F, j, F), c.tld(T_G, j, G);
-            tm_ld<2>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
-            VD w0 = VD(re) * ze[j][0] - ye[j][0], w1 = VD(re) * ze[j][1] - ye[j][1], w2 = VD(re) * ze[j][2] - ye[j][2];
+            tm_ld<8>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
+            const VD z0 = FIRST ? ze[j][0] : Q[HC_BE + 0], z1 = FIRST ? ze[j][1] : Q[HC_BE + 1],
+                     z2 = FIRST ? ze[j][2] : Q[HC_BE + 2];
+            VD w0 = VD(re) * z0 - ye[j][0], w1 = VD(re) * z1 - ye[j][1], w2 = VD(re) * z2 - ye[j][2];
             VD wb3 = F[FC_RHO + 3] * zb[j][3] - yb[j][3], wb4 = F[FC_RHO + 4] * zb[j][4] - yb[j][4];
             ru[j][0] = VD(sigma) * x[j][3] + G[GC_S + 3] * wb3 + G[GC_B31] * w2 - Q[0];
             ru[j][1] = VD(sigma) * x[j][4] + G[GC_S + 4] * wb4 + G[GC_B22] * w1 - Q[1];
@@ -1253,12 +1262,11 @@ struct ControlQP {
             VD xv[5] = {xt[j][0], xt[j][1], xt[j][2], utv, utk};
             // equality rows: l == u == b
             for (int q = 0; q < 3; ++q) {
-                VD zh = VD(alpha) * zte[q] + VD(1.0 - alpha) * ze[j][q];
                 VD zn = Hc[HC_BE + q];   // projection onto [b, b]
+                VD zh = VD(alpha) * zte[q] + VD(1.0 - alpha) * (FIRST ? ze[j][q] : zn);
                 VD dy = VD(re) * (zh - zn);
-                ze[j][q] = zn;
                 ye[j][q] = ye[j][q] + dy;
-                dye[j][q] = dy;
+                if (KEEP) dye[j][q] = dy;
             }
             for (int e = 0; e < 5; ++e) {
                 VD zt = G[GC_S + e] * xv[e];
@@ -1267,9 +1275,9 @@ struct ControlQP {
                 VD dy = F[FC_RHO + e] * (zh - zn);
                 zb[j][e] = zn;
                 yb[j][e] = yb[j][e] + dy;
-                dyb[j][e] = dy;
+                if (KEEP) dyb[j][e] = dy;
                 VD xn = VD(alpha) * xv[e] + VD(1.0 - alpha) * x[j][e];
-                if (keep_delta) dx[j][e] = xn - x[j][e];
+                if (KEEP) dx[j][e] = xn - x[j][e];
                 x[j][e] = xn;
             }
         }
@@ -1324,7 +1332,9 @@ struct ControlQP {
             VD S5[8], Q[2];
             tm_ld<8>(c.tm, j * T_STRIDE + T_G + GC_S, S5);
             tm_ld<2>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
-            for (int r = 0; r < 3; ++r) acc_row(v, ax[j][r], ze[j][r], c.ld(K_EEI + r, j));
+            // after at least one iteration the z of the equality rows is their right-hand side
+            for (int r = 0; r < 3; ++r)
+                acc_row(v, ax[j][r], tm_ld1(c.tm, j * T_STRIDE + T_H + HC_BE + r), c.ld(K_EEI + r, j));
             for (int e = 0; e < 5; ++e) {
                 acc_row(v, S5[e] * x[j][e], zb[j][e], c.ld(K_EBI + e, j));
                 VD q = (e >= 3) ? Q[e - 3] : VD(0.0);
@@ -1444,42 +1454,41 @@ struct ControlQP {
         factor();
         Norms N;
         int status = 0, iter = 0, updates = 0;
-        // same pass structure as SpeedQP::solve
-        int pass = 0;
+        // same structure as SpeedQP::solve
         bool checked = false, adapt = false, last = false;
-        // countdowns instead of iter % interval (a runtime integer division per test)
         int to_check = g.check_termination > 0 ? g.check_termination : -1;
         int to_adapt = (g.adaptive_rho && g.adaptive_rho_interval > 0) ? g.adaptive_rho_interval : -1;
         for (;;) {
-            if (pass == 0) {
-                ++iter;
-                checked = (--to_check == 0);
-                if (checked) to_check = g.check_termination;
-                adapt = (--to_adapt == 0);
-                if (adapt) to_adapt = g.adaptive_rho_interval;
-                last = iter >= g.max_iter;
-                iterate(checked || last);
-                if (checked || adapt || last) compute_norms(N);
-            }
-            if (pass > 0 || checked) {
-                status = check(N, pass == 2);
-                if (uni(status != 0)) break;
-            }
-            if (pass == 0) {
-                if (adapt) {
-                    double rn = rho_estimate(N, R.rho);
-                    if (uni(rn > R.rho * g.adaptive_rho_tolerance || rn < R.rho / g.adaptive_rho_tolerance)) {
-                        R.set(rn);
-                        ++updates;
-                        factor();
+            ++iter;
+            checked = (--to_check == 0);
+            if (checked) to_check = g.check_termination;
+            adapt = (--to_adapt == 0);
+            if (adapt) to_adapt = g.adaptive_rho_interval;
+            last = iter >= g.max_iter;
+            const bool slow = checked || adapt || last;
+            if (iter == 1 || slow) {
+                if (iter == 1) iterate<true, true>();
+                else iterate<false, true>();
+                if (slow) {
+                    compute_norms(N);
+                    if (checked) status = check(N, 0);
+                    if (uni(status == 0) && adapt) {
+                        double rn = rho_estimate(N, R.rho);
+                        if (uni(rn > R.rho * g.adaptive_rho_tolerance || rn < R.rho / g.adaptive_rho_tolerance)) {
+                            R.set(rn);
+                            ++updates;
+                            factor();
+                        }
                     }
+                    if (uni(status == 0) && last) {
+                        if (!checked) status = check(N, 0);
+                        if (uni(status == 0)) status = check(N, 1);
+                        if (uni(status == 0)) status = ACMPC_MAX_ITER_REACHED;
+                    }
+                    if (uni(status != 0)) break;
                 }
-                if (last) pass = checked ? 2 : 1;
-            } else if (pass == 1) {
-                pass = 2;
             } else {
-                status = ACMPC_MAX_ITER_REACHED;
-                break;
+                iterate<false, false>();
             }
         }
         info.status = status, info.iter = iter, info.rho_updates = updates;
@@ -1503,7 +1512,7 @@ struct ControlQP {
                 }
                 for (int r = 0; r < 3; ++r) {
                     st_lane(wrow + ((15 + r) * C + j) * 32, ye[j][r]);
-                    st_lane(wrow + ((18 + r) * C + j) * 32, ze[j][r]);
+                    st_lane(wrow + ((18 + r) * C + j) * 32, tm_ld1(c.tm, j * T_STRIDE + T_H + HC_BE + r));
                 }
             }
             AC_LANE0

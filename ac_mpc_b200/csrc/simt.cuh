@@ -353,8 +353,9 @@ AC_DEV VD vsqrt(double a) { return sqrt(a); }
 AC_DEV VD vsin(double a) { return sin(a); }
 AC_DEV VD vcos(double a) { return cos(a); }
 AC_DEV VD vatan(double a) { return atan(a); }
-AC_DEV VD vmax(double a, double b) { return fmax(a, b); }
-AC_DEV VD vmin(double a, double b) { return fmin(a, b); }
+// compare-select instead of fmax/fmin: no NaN-quieting sequence (the operands here are never NaN)
+AC_DEV VD vmax(double a, double b) { return a > b ? a : b; }
+AC_DEV VD vmin(double a, double b) { return a < b ? a : b; }
 AC_DEV VD vatan2(double y, double x) { return atan2(y, x); }
 AC_DEV VD vfmod(double a, double b) { return fmod(a, b); }
 
@@ -373,13 +374,29 @@ AC_DEV VD shfl_up_raw(double a, int d) { return __shfl_up_sync(kFull, a, d); }
 AC_DEV VD shfl_down_raw(double a, int d) { return __shfl_down_sync(kFull, a, d); }
 AC_DEV VD shfl_rot_up1(double a) { return __shfl_sync(kFull, a, ((int)(threadIdx.x & 31) + 31) & 31); }
 AC_DEV bool uni(bool p) { return __any_sync(kFull, p) != 0; }
-AC_DEV VD vrsqrt(double a) { return rsqrt(a); }
+// 1/sqrt(a) for a normal, positive a (the equilibration norms are clamped to [1e-4, 1e4]): hardware seed
+// (MUFU.RSQ64H, ~20 bits) + three Newton steps, fully inline -- CUDA's rsqrt() calls a helper per value
+AC_DEV VD vrsqrt(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double e = fma(-(h * y), y, 0.5);
+        y = fma(y, e, y);
+    }
+    return y;
+}
 AC_DEV double lane_value(double a, int src) { return __shfl_sync(kFull, a, src); }
 
 AC_DEV double wmax(double v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_xor_sync(kFull, v, o);
+        v = v > t ? v : t;
+    }
     return v;
 }
 AC_DEV double wsum(double v)

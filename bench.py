@@ -307,7 +307,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     # pattern, get_control on ONE object whose OSQP state persists (here: the handle's warm-start record).
     cl = tracks.synthetic_centreline(args.track)
     p1 = tracks.make_instances(cl, [0], H)[0]
-    seq = tracks.make_instances(cl, (np.arange(args.latency_reps + 20) * 4) % cl.shape[0], H)   # 2 m per step
+    seq = tracks.make_instances(cl, (np.arange(max(args.latency_reps, 40) + 20) * 4) % cl.shape[0], H)   # 2 m per step
 
     def p50(fn, n):
         ts = []
