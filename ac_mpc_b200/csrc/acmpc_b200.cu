@@ -128,16 +128,17 @@ __device__ __forceinline__ acmpc::InstanceOut slice_outputs(const acmpc_outputs&
 // small code, high occupancy.  Hands the speed profile to kernel 2 through p.vel ([B,n], = out.v_ref when
 // the caller asked for that field).
 template <int C>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 3) acmpc_speed_kernel(const __grid_constant__ KernelParams p)
+__global__ void __launch_bounds__(32, 12) acmpc_speed_kernel(const __grid_constant__ KernelParams p)
 {
+    // one warp = one CTA: instances need 25..100+ iterations, and a multi-warp CTA would hold its slots until its
+    // slowest warp is done
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * kWarpsPerCta + warp;
-    if (b >= p.B) return;
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x;
     const int H = p.cfg.horizon, n = H - 1;
     acmpc::Ctx<C> c;
     c.S = nullptr;
-    c.W = reinterpret_cast<double*>(smem_raw + (size_t)warp * warp_smem_bytes_speed<C>());
+    c.W = reinterpret_cast<double*>(smem_raw);
     c.tm.a = 0;
     c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(c.W + acmpc::Layout<C>::kSpeedDoubles);
@@ -323,10 +324,10 @@ const void* speed_kernel_for(int H)
 size_t speed_smem_bytes_for(int H)
 {
     switch (stages_per_lane(H)) {
-        case 1: return kWarpsPerCta * warp_smem_bytes_speed<1>();
-        case 2: return kWarpsPerCta * warp_smem_bytes_speed<2>();
-        case 3: return kWarpsPerCta * warp_smem_bytes_speed<3>();
-        default: return kWarpsPerCta * warp_smem_bytes_speed<4>();
+        case 1: return warp_smem_bytes_speed<1>();
+        case 2: return warp_smem_bytes_speed<2>();
+        case 3: return warp_smem_bytes_speed<3>();
+        default: return warp_smem_bytes_speed<4>();
     }
 }
 
@@ -365,9 +366,7 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
         if (h->ev_count < kEventRing) ++h->ev_count;
         cudaEventRecord(ev[0], stream);
     }
-    const int speed_ctas = (B + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (fail(h, cudaLaunchKernel(speed_kernel_for(H), dim3(speed_ctas), dim3(32 * kWarpsPerCta), args,
-                                 speed_smem_bytes_for(H), stream),
+    if (fail(h, cudaLaunchKernel(speed_kernel_for(H), dim3(B), dim3(32), args, speed_smem_bytes_for(H), stream),
              "speed kernel launch"))
         return ACMPC_ERR_CUDA;
     if (ev) cudaEventRecord(ev[1], stream);
