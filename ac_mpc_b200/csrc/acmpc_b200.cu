@@ -41,43 +41,51 @@ struct KernelParams {
     uint32_t queue_base;
     uint32_t warps_launched;
     int32_t persistent;   // 0: one instance per warp, grid = ceil(B/4) CTAs (warps of a CTA stay in phase)
+    // Longest-first scheduling (NULL = instance order).  order = [2 x 8 counters | 4 bins x B ids | 4 bins x B ids]:
+    // counters 0..3 / bins "a" order the speed kernel's CTAs by the live v_max (higher limit = more ADMM
+    // iterations), counters 4..7 / bins "b" are filled BY the speed kernel with its iteration count class and
+    // order the control kernel's work queue (the control QP of a long speed solve is usually long too).
+    // Two counter sets alternate between launches: the control kernel zeroes the set of the NEXT launch.
+    int32_t* order;
+    int32_t order_set;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p)
+constexpr int kOrderBins = 4;
+
+// item t of a binned order -> instance id
+__device__ __forceinline__ int ordered_instance(const int32_t* cnt, const int32_t* bins, int B, int t)
 {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < kOrderBins - 1; ++i) {
+        const int c = cnt[i];
+        if (k == i && t >= c) t -= c, k = i + 1;
+    }
+    return bins[(size_t)k * B + t];
 }
 
-// Stage `bytes` (multiple of 16, both ends 16-byte aligned) global -> shared through the TMA engine.
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* mbar, int lane)
+// `cnt` = the launch's counter set, `bins` = order + 16
+__global__ void acmpc_order_kernel(const double* __restrict__ vmax, int B, double v_lo, double v_hi, int32_t* cnt,
+                                   int32_t* bins)
 {
-    const uint32_t bar = smem_u32(mbar);
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                smem_u32(dst)),
-            "l"(src), "r"(bytes), "r"(bar)
-            : "memory");
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = -1;
+    if (b < B) {
+        const double f = (vmax[b] - v_lo) / (v_hi - v_lo);
+        k = kOrderBins - 1 - (int)(f * kOrderBins);          // highest limit first
+        k = k < 0 ? 0 : (k > kOrderBins - 1 ? kOrderBins - 1 : k);
     }
-    __syncwarp();
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar)
-            : "memory");
+    // one atomic per (warp, bin) instead of one per instance
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < kOrderBins; ++i) {
+        const unsigned m = __ballot_sync(0xffffffffu, k == i);
+        if (m == 0) continue;
+        int base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(cnt + i, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (k == i) bins[(size_t)i * B + base + __popc(m & ((1u << lane) - 1))] = b;
     }
-    // the barrier word is re-initialised for the warp's next instance
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-    __syncwarp();
 }
 
 constexpr int kEventRing = 256;
@@ -134,7 +142,8 @@ __global__ void __launch_bounds__(32, 16) acmpc_speed_kernel(const __grid_consta
     // slowest warp is done
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
-    const int b = blockIdx.x;
+    int32_t* cnt = p.order ? p.order + 8 * p.order_set : nullptr;
+    const int b = (p.order && p.vmax) ? ordered_instance(cnt, p.order + 16, p.B, blockIdx.x) : (int)blockIdx.x;
     const int H = p.cfg.horizon, n = H - 1;
     acmpc::Ctx<C> c;
     c.S = nullptr;
@@ -145,8 +154,15 @@ __global__ void __launch_bounds__(32, 16) acmpc_speed_kernel(const __grid_consta
     stage_path(c.W, p.paths + (size_t)b * 3 * H, H, p.use_tma, mbar, lane);
     const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
     double* wrec = p.warm ? p.warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;
-    acmpc::speed_instance<C>(c, c.W, vmax, p.is_localised, p.vel + (size_t)b * n, slice_outputs(p.out, b, H), wrec,
-                             p.use_warm != 0);
+    const int iters = acmpc::speed_instance<C>(c, c.W, vmax, p.is_localised, p.vel + (size_t)b * n,
+                                               slice_outputs(p.out, b, H), wrec, p.use_warm != 0);
+    if (p.order && lane == 0) {   // class of this solve for the control kernel's queue: most iterations first
+        const int per = p.cfg.check_termination > 0 ? p.cfg.check_termination : 25;
+        int k = kOrderBins - iters / per;
+        k = k < 0 ? 0 : (k > kOrderBins - 1 ? kOrderBins - 1 : k);
+        const int pos = atomicAdd(cnt + 4 + k, 1);
+        p.order[16 + (size_t)(kOrderBins + k) * p.B + pos] = b;
+    }
 }
 
 // Kernel 2: control QP + unpack + rollout + cost.
@@ -165,12 +181,16 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C == 2 ? 2 :
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (p.order && blockIdx.x == 0 && threadIdx.x < 8) p.order[8 * (1 - p.order_set) + threadIdx.x] = 0;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // optionally persistent warps: the first instance is the warp's global index, further ones come from the
     // queue, so a warp whose instance converges early does not idle behind its CTA's slowest one
-    for (int b = blockIdx.x * kWarpsPerCta + warp; b < p.B;) {
+    for (int item = blockIdx.x * kWarpsPerCta + warp; item < p.B;) {
+        const int b = p.order ? ordered_instance(p.order + 8 * p.order_set + 4, p.order + 16 + (size_t)kOrderBins * p.B,
+                                                 p.B, item)
+                              : item;
         const int H = p.cfg.horizon, n = H - 1;
         acmpc::Ctx<C> c;
         c.S = reinterpret_cast<double*>(smem_raw + (size_t)warp * warp_smem_bytes<C>());
@@ -189,7 +209,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C == 2 ? 2 :
         if (lane == 0) ticket = atomicAdd(p.queue, 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         const uint32_t next = (ticket - p.queue_base) + p.warps_launched;
-        b = next < (uint32_t)p.B ? (int)next : p.B;
+        item = next < (uint32_t)p.B ? (int)next : p.B;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -224,6 +244,10 @@ struct acmpc_handle {
     // device arena for the host entry point
     void* d_arena;
     size_t arena_bytes;
+    int32_t* d_order[4];     // longest-first order buffers (one per chunk stream), see KernelParams::order
+    size_t order_cap[4];     // instances each can hold
+    int order_parity[4];     // counter set of the last launch
+    int order_on;            // ACMPC_ORDER=0 switches the ordering off
     void* d_warm;            // warm-start records of the host entry point (keep_warm)
     int warm_B;
     void* d_vel;             // speed-profile hand-over buffer of the device entry point (when v_ref is not requested)
@@ -331,6 +355,23 @@ size_t speed_smem_bytes_for(int H)
     }
 }
 
+// (re)allocate the order buffer of chunk stream `qi` for B instances; synchronous, only when it has to grow
+bool ensure_order(acmpc_handle* h, int qi, int B)
+{
+    if (!h->order_on || B < 1024 || (size_t)B <= h->order_cap[qi]) return true;
+    if (h->d_order[qi]) {
+        if (fail(h, cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return false;
+        cudaFree(h->d_order[qi]);
+    }
+    h->d_order[qi] = nullptr, h->order_cap[qi] = 0;
+    const size_t ints = 16 + 2 * (size_t)kOrderBins * B;
+    if (fail(h, cudaMalloc(&h->d_order[qi], ints * sizeof(int32_t)), "cudaMalloc(order)") ||
+        fail(h, cudaMemset(h->d_order[qi], 0, 16 * sizeof(int32_t)), "cudaMemset(order)"))
+        return false;
+    h->order_cap[qi] = (size_t)B;
+    return true;
+}
+
 // Two launches on `stream`: the speed-profile kernel, then the control kernel.  `d_vel` [B,n] is the
 // hand-over buffer between them.
 int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offsets, const double* d_vmax,
@@ -359,6 +400,17 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     if (getenv("ACMPC_DEBUG")) fprintf(stderr, "acmpc launch: B=%d ctas=%d ctas_per_sm=%d sms=%d smem=%zu\n", B, ctas, h->ctas_per_sm, h->sm_count, smem);
     p.queue = h->d_queue + qi, p.queue_base = h->queue_pos[qi], p.warps_launched = (uint32_t)(ctas * kWarpsPerCta);
     if (p.persistent) h->queue_pos[qi] += (uint32_t)B;   // every solved instance draws one ticket
+    // longest-first order for batches that run several rounds of the device (see KernelParams::order)
+    p.order = nullptr;
+    if (h->order_on && B >= 1024 && h->d_order[qi] && (size_t)B <= h->order_cap[qi]) {
+        p.order = h->d_order[qi];
+        p.order_set = (h->order_parity[qi] ^= 1);
+        if (d_vmax) {
+            acmpc_order_kernel<<<(B + 255) / 256, 256, 0, stream>>>(d_vmax, B, h->cfg.v_min, h->cfg.v_max,
+                                                                    p.order + 8 * p.order_set, p.order + 16);
+            h->last_launches += 1;
+        }
+    }
     cudaEvent_t* ev = nullptr;
     if (h->profiling && h->ev) {
         ev = h->ev + 3 * h->ev_head;
@@ -433,6 +485,11 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
     for (int k = 0; k < 4; ++k) h->queue_pos[k] = 0, h->streams[k] = nullptr;
     h->d_vel = nullptr, h->vel_bytes = 0;
     h->d_warm = nullptr, h->warm_B = 0;
+    for (int k = 0; k < 4; ++k) h->d_order[k] = nullptr, h->order_cap[k] = 0, h->order_parity[k] = 0;
+    {
+        const char* e = getenv("ACMPC_ORDER");
+        h->order_on = (e && e[0] == '0') ? 0 : 1;
+    }
     h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
     {
         const char* e = getenv("ACMPC_PERSISTENT");
@@ -490,6 +547,8 @@ int32_t acmpc_destroy(acmpc_handle* h)
     if (h->d_queue) cudaFree(h->d_queue);
     if (h->d_vel) cudaFree(h->d_vel);
     if (h->d_warm) cudaFree(h->d_warm);
+    for (int k = 0; k < 4; ++k)
+        if (h->d_order[k]) cudaFree(h->d_order[k]);
     if (h->ev) {
         for (int i = 0; i < 3 * kEventRing; ++i) cudaEventDestroy(h->ev[i]);
         delete[] h->ev;
@@ -524,6 +583,7 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
     if (B == 0) return ACMPC_OK;
     if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
     h->last_launches = 0;
+    if (!ensure_order(h, 0, B)) return ACMPC_ERR_CUDA;
     double* d_vel = d_out->v_ref;
     if (!d_vel) {   // the caller did not ask for v_ref: hand over through a scratch buffer owned by the handle
         const size_t need = (size_t)B * (h->cfg.horizon - 1) * sizeof(double);
@@ -534,6 +594,11 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
             }
             h->d_vel = nullptr, h->vel_bytes = 0;
     h->d_warm = nullptr, h->warm_B = 0;
+    for (int k = 0; k < 4; ++k) h->d_order[k] = nullptr, h->order_cap[k] = 0, h->order_parity[k] = 0;
+    {
+        const char* e = getenv("ACMPC_ORDER");
+        h->order_on = (e && e[0] == '0') ? 0 : 1;
+    }
     h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
             if (fail(h, cudaMalloc(&h->d_vel, need), "cudaMalloc(vel)")) return ACMPC_ERR_CUDA;
             h->vel_bytes = need;
@@ -600,6 +665,7 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
         if (cb <= 0) break;
         cudaStream_t s = h->streams[k];
         const size_t z = (size_t)c0, nbk = (size_t)cb;
+        if (!ensure_order(h, k, cb)) return ACMPC_ERR_CUDA;
         if (fail(h, cudaMemcpyAsync(base + o_paths + z * 3 * H * 8, paths + z * 3 * H, nbk * 3 * H * 8,
                                     cudaMemcpyHostToDevice, s), "H2D paths"))
             return ACMPC_ERR_CUDA;

@@ -1538,8 +1538,8 @@ struct InstanceOut {
 // region only.  `vel_out` [n] always receives the profile (zeros unless the QP status is "solved",
 // spatial_mpc.py:115-122); it is the hand-over to phase 2.
 template <int C>
-AC_DEV void speed_instance(const Ctx<C>& c, const double* raw_path, double v_max_live, int localised,
-                           double* vel_out, const InstanceOut& o, double* warm = nullptr, bool use_warm = false)
+AC_DEV int speed_instance(const Ctx<C>& c, const double* raw_path, double v_max_live, int localised,
+                          double* vel_out, const InstanceOut& o, double* warm = nullptr, bool use_warm = false)
 {
     const int n = c.n;
     PathRegs<C> path;
@@ -1573,6 +1573,7 @@ AC_DEV void speed_instance(const Ctx<C>& c, const double* raw_path, double v_max
         if (o.iters) o.iters[0] = si.iter;
         if (o.rho_updates) o.rho_updates[0] = si.rho_updates;
     }
+    return si.iter;   // ADMM iterations of the speed-profile QP (a scheduling hint for phase 2)
 }
 
 // Phase 2: control QP, unpack, rollout, cost (spatial_mpc.py:186-212).  The waypoints are rebuilt from the

@@ -136,8 +136,10 @@ int32_t acmpc_solve_batch_host(acmpc_handle *h, int32_t B, const double *paths,
                                const double *offsets, const double *vmax, int32_t is_localised,
                                int32_t keep_warm, const acmpc_outputs *out);
 
-/* Counters of the last call: kernel launches issued (2: speed-profile kernel + control kernel), dynamic shared
- * memory per CTA of the control kernel, threads per CTA, instances per CTA. */
+/* Counters of the last call: kernel launches issued (per chunk: speed-profile kernel + control kernel, plus the
+ * small ordering kernel for batches of 1024+ with per-instance v_max; the host entry point splits batches of
+ * 512+ / 2048+ into 2 / 4 chunks), dynamic shared memory per CTA of the control kernel, threads per CTA,
+ * instances per CTA. */
 int32_t acmpc_last_launch_info(const acmpc_handle *h, int32_t *n_launches, int32_t *smem_bytes,
                                int32_t *threads_per_cta, int32_t *instances_per_cta);
 
