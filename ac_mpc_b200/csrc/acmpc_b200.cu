@@ -50,6 +50,43 @@ struct KernelParams {
     int32_t order_set;
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Stage `bytes` (multiple of 16, both ends 16-byte aligned) global -> shared through the TMA engine.
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* mbar, int lane)
+{
+    const uint32_t bar = smem_u32(mbar);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(dst)),
+            "l"(src), "r"(bytes), "r"(bar)
+            : "memory");
+    }
+    __syncwarp();
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+    }
+    // the barrier word is re-initialised for the warp's next instance
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+    __syncwarp();
+}
+
 constexpr int kOrderBins = 4;
 
 // item t of a binned order -> instance id
@@ -248,6 +285,7 @@ struct acmpc_handle {
     size_t order_cap[4];     // instances each can hold
     int order_parity[4];     // counter set of the last launch
     int order_on;            // ACMPC_ORDER=0 switches the ordering off
+    int chunk_pct[3];        // share of the first three chunks of a 4-chunk host call, in percent
     void* d_warm;            // warm-start records of the host entry point (keep_warm)
     int warm_B;
     void* d_vel;             // speed-profile hand-over buffer of the device entry point (when v_ref is not requested)
@@ -489,6 +527,9 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
     {
         const char* e = getenv("ACMPC_ORDER");
         h->order_on = (e && e[0] == '0') ? 0 : 1;
+        h->chunk_pct[0] = 25, h->chunk_pct[1] = 25, h->chunk_pct[2] = 25;
+        const char* c = getenv("ACMPC_CHUNKS");   // e.g. "25,25,25" (experiments)
+        if (c) sscanf(c, "%d,%d,%d", &h->chunk_pct[0], &h->chunk_pct[1], &h->chunk_pct[2]);
     }
     h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
     {
@@ -598,6 +639,9 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
     {
         const char* e = getenv("ACMPC_ORDER");
         h->order_on = (e && e[0] == '0') ? 0 : 1;
+        h->chunk_pct[0] = 25, h->chunk_pct[1] = 25, h->chunk_pct[2] = 25;
+        const char* c = getenv("ACMPC_CHUNKS");   // e.g. "25,25,25" (experiments)
+        if (c) sscanf(c, "%d,%d,%d", &h->chunk_pct[0], &h->chunk_pct[1], &h->chunk_pct[2]);
     }
     h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
             if (fail(h, cudaMalloc(&h->d_vel, need), "cudaMalloc(vel)")) return ACMPC_ERR_CUDA;
@@ -653,15 +697,21 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
     // Large batches go through as up to 4 chunks on 4 streams (own ticket queue each), so that the H2D copy of
     // one chunk and the D2H copy of another overlap the kernels of a third.  (Async only from pinned host memory.)
     const int chunks = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
-    const int per = ((B + chunks - 1) / chunks + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
+    // chunk boundaries (equal quarters measured best; ACMPC_CHUNKS=a,b,c overrides the first three shares)
+    int bound[5] = {0, B, B, B, B};
+    if (chunks == 2) bound[1] = B / 2 / kWarpsPerCta * kWarpsPerCta;
+    if (chunks == 4) {
+        const int pct[3] = {h->chunk_pct[0], h->chunk_pct[0] + h->chunk_pct[1], h->chunk_pct[0] + h->chunk_pct[1] + h->chunk_pct[2]};
+        for (int k = 0; k < 3; ++k) bound[k + 1] = (int)((long long)B * pct[k] / 100) / kWarpsPerCta * kWarpsPerCta;
+    }
     const size_t wstride = warm_bytes_for(H);
     h->last_launches = 0;
     if (h->d_warm && chunks > 1 &&
         fail(h, cudaStreamSynchronize(h->streams[0]), "cudaStreamSynchronize"))   // the zero-fill of new records
         return ACMPC_ERR_CUDA;
     for (int k = 0; k < chunks; ++k) {
-        const int c0 = k * per;
-        const int cb = (c0 + per <= B) ? per : B - c0;
+        const int c0 = bound[k];
+        const int cb = bound[k + 1] - c0;
         if (cb <= 0) break;
         cudaStream_t s = h->streams[k];
         const size_t z = (size_t)c0, nbk = (size_t)cb;
