@@ -301,3 +301,22 @@ def test_warm_start_closed_loop_replay_matches_oracle_objects():
     torch.cuda.synchronize()
     assert np.array_equal(views["iters"].cpu().numpy(), cold["iters"])
     assert np.array_equal(views["controls"].cpu().numpy(), cold["controls"])
+
+
+def test_large_batch_131072_instances():
+    """One launch far beyond what the device holds at once (work queue + longest-first order over ~110 rounds):
+    every instance solved exactly once, a random sample checked against the oracle."""
+    B = 131072
+    base, vm = tracks.perturbed_batch("monza", 8192, seed=12)
+    rep = B // base.shape[0]
+    paths, vmax = np.tile(base, (rep, 1, 1)), np.tile(vm, rep)
+    mpc = _solver()
+    out = mpc.solve_host(paths, None, vmax, fields=["controls", "status", "iters", "cost"])
+    # the batch is 16 copies of the same 8192 instances: every copy must give bit-identical results
+    for k in ("controls", "status", "iters", "cost"):
+        a = out[k].reshape((rep, base.shape[0]) + out[k].shape[1:])
+        assert np.array_equal(a, np.broadcast_to(a[0], a.shape)), k
+    sub = np.random.default_rng(2).choice(base.shape[0], 512, replace=False)
+    want = port.solve_batch(port.default_config(), base[sub], None, vm[sub], nthreads=16)
+    assert np.array_equal(out["iters"][sub], want["iters"])
+    np.testing.assert_allclose(out["controls"][sub], want["controls"], rtol=0, atol=TOL)
