@@ -806,8 +806,9 @@ struct ControlQP {
     VI cls[C];   // class of bound row j in bits 2j, 2j+1
     double cs, cinv, nq_unscaled, nq_scaled;
     RhoSet R;
+    bool bad_bounds;   // some row has l > u: OSQP refuses the data (setup / update fail), nothing is solved
 
-    AC_MEM explicit ControlQP(const Ctx<C>& ctx) : c(ctx), n(ctx.n), H(ctx.H) {}
+    AC_MEM explicit ControlQP(const Ctx<C>& ctx) : c(ctx), n(ctx.n), H(ctx.H), bad_bounds(false) {}
 
     // linearise + stack (dynamics.py:65-103, solvers/control.py:26-79), OSQP scale_data (Ruiz) and
     // set_rho_vec classes; the scaled problem goes to tensor memory (chunks G, H) and shared memory (cold).
@@ -947,6 +948,7 @@ struct ControlQP {
             VI bits = vi_all(0);
             for (int e = 0; e < 5; ++e) {
                 VB real = (e < 3) ? isx : hasU;
+                if (wany(real & (lo[e] > hi[e]))) bad_bounds = true;
                 VD l = vsel(real, lo[e] * EB[j][e], VD(0.0)), u = vsel(real, hi[e] * EB[j][e], VD(0.0));
                 bits = bits | (row_class(l, u) << (2 * e));
                 Hc[HC_LB + e] = l, Hc[HC_UB + e] = u;
@@ -1431,6 +1433,14 @@ struct ControlQP {
     AC_MEM void solve(SolveInfo& info, double* warm, bool use_warm)
     {
         const acmpc_config& g = *c.cfg;
+        if (uni(bad_bounds)) {   // osqp_setup / osqp_update_bounds reject l > u: no solve, solver state untouched
+            info.status = ACMPC_UNSOLVED, info.iter = 0, info.rho_updates = 0;
+            info.pri_res = info.dua_res = info.obj_val = 0.0;
+            AC_UNROLL
+            for (int j = 0; j < C; ++j)
+                for (int e = 0; e < 5; ++e) x[j][e] = VD(0.0);
+            return;
+        }
         double* wrow = warm ? warm + WR_HEADER + 2 * WR_SPEED_FIELDS * C * 32 : nullptr;
         const bool have = warm && use_warm && warm[WR_VALID + 2] != 0.0;
         R.set(have ? warm[WR_RHO + 2] : clampu(g.rho, kRhoMin, kRhoMax));

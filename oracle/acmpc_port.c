@@ -264,7 +264,11 @@ static int solve_ws(opq_workspace **ws, const opq_settings *st, int warm, int n,
 {
     if (*ws == NULL) {
         *ws = opq_setup(n, m, Pp, Pi, Px, q, Ap, Ai, Ax, l, u, st);
-        if (*ws == NULL) return OPQ_UNSOLVED;
+        if (*ws == NULL) {   /* data rejected (l > u): the reference's osqp.setup raises */
+            memset(info, 0, sizeof(*info));
+            info->status = OPQ_UNSOLVED;
+            return OPQ_UNSOLVED;
+        }
     } else {
         if (!warm) opq_cold_start(*ws);
         if (opq_update(*ws, q, l, u, Ax) != 0) {

@@ -497,6 +497,10 @@ opq_workspace *opq_setup(int n, int m, const int *Pp, const int *Pi, const doubl
                          const double *q, const int *Ap, const int *Ai, const double *Ax,
                          const double *l, const double *u, const opq_settings *settings)
 {
+    /* validate_data: "Lower bound must be lower than or equal to upper bound" -- osqp_setup fails (the Python
+     * wrapper raises ValueError); osqp_update_bounds applies the same test (opq_update below) */
+    for (int i = 0; i < m; i++)
+        if (l[i] > u[i]) return NULL;
     opq_workspace *w = (opq_workspace *)calloc(1, sizeof(*w));
     w->n = n, w->m = m, w->N = n + m;
     w->s = *settings;

@@ -320,3 +320,34 @@ def test_large_batch_131072_instances():
     want = port.solve_batch(port.default_config(), base[sub], None, vm[sub], nthreads=16)
     assert np.array_equal(out["iters"][sub], want["iters"])
     np.testing.assert_allclose(out["controls"][sub], want["controls"], rtol=0, atol=TOL)
+
+
+SETTINGS = [dict(scaling=0), dict(scaling=3), dict(check_termination=1), dict(check_termination=10),
+            dict(check_termination=7, adaptive_rho_interval=20), dict(adaptive_rho=0), dict(adaptive_rho_interval=25),
+            dict(alpha=1.0), dict(rho=1.0), dict(eps_abs=1e-5, eps_rel=1e-5), dict(max_iter=60), dict(max_iter=1),
+            dict(check_termination=0, max_iter=80)]
+
+
+@pytest.mark.parametrize("kw", SETTINGS, ids=[",".join(f"{k}={v}" for k, v in s.items()) for s in SETTINGS])
+def test_osqp_settings_sweep_matches_oracle(kw):
+    """Every OSQP setting of acmpc_config away from its default (see the emulation test of the same name)."""
+    paths, vmax = tracks.perturbed_batch("monza", 96, seed=7)
+    got = _solver(**kw).solve_host(paths, None, vmax, False)
+    want = port.solve_batch(port.default_config(**kw), paths, None, vmax, False, nthreads=8)
+    for k in ("status", "status_speed", "iters", "rho_updates"):
+        assert np.array_equal(got[k], want[k]), k
+    ok = (want["status"] == 1) & (want["status_speed"] == 1)
+    if ok.any():
+        np.testing.assert_allclose(got["controls"][ok], want["controls"][ok], rtol=0, atol=TOL)
+    np.testing.assert_allclose(got["cost"], want["cost"], rtol=1e-7, atol=1e-7)
+
+
+def test_track_narrower_than_the_car_is_rejected_like_osqp_does():
+    paths, vmax = tracks.perturbed_batch("monza", 16, seed=7)
+    narrow = paths.copy()
+    narrow[:, :, 2] = 1.9
+    got = _solver().solve_host(narrow, None, vmax)
+    want = port.solve_batch(port.default_config(), narrow, None, vmax, nthreads=2)
+    assert np.all(got["status"] == -10) and np.all(want["status"] == -10)
+    assert np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["status_speed"], want["status_speed"])
+    np.testing.assert_allclose(got["v_ref"], want["v_ref"], rtol=0, atol=TOL)

@@ -71,3 +71,50 @@ def test_warm_batch_matches_oracle_sequences_with_mixed_localisation():
             assert got["iters"][b].tolist() == want["iters"].tolist(), (t, b)
             assert got["status"][b] == want["status"]
             np.testing.assert_allclose(got["controls"][b], want["controls"], rtol=0, atol=1e-8)
+
+
+SETTINGS = [dict(), dict(scaling=0), dict(scaling=3), dict(check_termination=1), dict(check_termination=10),
+            dict(check_termination=7, adaptive_rho_interval=20), dict(adaptive_rho=0), dict(adaptive_rho_interval=25),
+            dict(alpha=1.0), dict(rho=1.0), dict(eps_abs=1e-5, eps_rel=1e-5), dict(max_iter=60), dict(max_iter=1),
+            dict(check_termination=0, max_iter=80)]
+
+
+@pytest.mark.parametrize("kw", SETTINGS, ids=[",".join(f"{k}={v}" for k, v in s.items()) or "default" for s in SETTINGS])
+def test_osqp_settings_sweep_matches_oracle(kw):
+    """Every OSQP setting the config exposes, away from its default: check cadence (incl. every iteration and
+    never), adaptive-rho cadence not a multiple of the check cadence, no equilibration, tight tolerances (the
+    QP is infeasible as posed: primal-infeasibility certificates), iteration caps."""
+    from ac_mpc_b200 import tracks
+
+    paths, vmax = tracks.perturbed_batch("monza", 24, seed=7)
+    cfg = port.default_config(**kw)
+    a = _emul.solve_batch(cfg, paths, None, vmax, False)
+    b = port.solve_batch(cfg, paths, None, vmax, False, nthreads=4)
+    for k in ("status", "status_speed", "iters", "rho_updates"):
+        assert np.array_equal(a[k], b[k]), k
+    ok = (b["status"] == 1) & (b["status_speed"] == 1)
+    if ok.any():
+        assert np.abs(a["controls"] - b["controls"])[ok].max() < 1e-8
+    np.testing.assert_allclose(a["cost"], b["cost"], rtol=1e-7, atol=1e-7)
+
+
+def test_track_narrower_than_the_car_is_rejected_like_osqp_does():
+    """width/2 < vehicle margin makes l > u on every e_y row: osqp.setup / update refuse such data (the
+    reference would see a ValueError); oracle and kernel report status 'unsolved' (-10) and iterate nothing.
+    A width that leaves less than 1e-4 m of room turns those rows into OSQP's equality class instead."""
+    from ac_mpc_b200 import tracks
+
+    paths, vmax = tracks.perturbed_batch("monza", 8, seed=7)
+    cfg = port.default_config()
+    narrow = paths.copy()
+    narrow[:, :, 2] = 1.9
+    a = _emul.solve_batch(cfg, narrow, None, vmax, False)
+    b = port.solve_batch(cfg, narrow, None, vmax, False, nthreads=2)
+    assert np.all(a["status"] == -10) and np.all(b["status"] == -10)
+    assert np.all(a["iters"][:, 1] == 0) and np.array_equal(a["iters"], b["iters"])
+    tight = paths.copy()
+    tight[:, :, 2] = 1.99 + 5e-5
+    a = _emul.solve_batch(cfg, tight, None, vmax, False)
+    b = port.solve_batch(cfg, tight, None, vmax, False, nthreads=2)
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iters"], b["iters"])
+    assert np.abs(a["controls"] - b["controls"]).max() < 1e-8
