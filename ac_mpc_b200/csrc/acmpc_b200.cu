@@ -281,6 +281,8 @@ struct acmpc_handle {
     // device arena for the host entry point
     void* d_arena;
     size_t arena_bytes;
+    void* h_stage;           // pinned mirror of the arena for small batches (one H2D + one D2H)
+    size_t stage_bytes;
     int32_t* d_order[4];     // longest-first order buffers (one per chunk stream), see KernelParams::order
     size_t order_cap[4];     // instances each can hold
     int order_parity[4];     // counter set of the last launch
@@ -507,6 +509,7 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
     h->cfg = *cfg;
     h->device = device;
     h->d_arena = nullptr, h->arena_bytes = 0;
+    h->h_stage = nullptr, h->stage_bytes = 0;
     h->last_launches = h->last_smem = h->last_threads = h->last_ipc = 0;
     cudaDeviceProp prop;
     if (fail(h, cudaSetDevice(device), "cudaSetDevice") ||
@@ -585,6 +588,7 @@ int32_t acmpc_destroy(acmpc_handle* h)
     if (!h) return ACMPC_OK;
     cudaSetDevice(h->device);
     if (h->d_arena) cudaFree(h->d_arena);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->d_queue) cudaFree(h->d_queue);
     if (h->d_vel) cudaFree(h->d_vel);
     if (h->d_warm) cudaFree(h->d_warm);
@@ -690,10 +694,71 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
     if (off > h->arena_bytes) {
         if (h->d_arena) cudaFree(h->d_arena);
         h->d_arena = nullptr, h->arena_bytes = 0;
+    h->h_stage = nullptr, h->stage_bytes = 0;
         if (fail(h, cudaMalloc(&h->d_arena, off), "cudaMalloc(arena)")) return ACMPC_ERR_CUDA;
         h->arena_bytes = off;
     }
     char* base = static_cast<char*>(h->d_arena);
+    const size_t wstride = warm_bytes_for(H);
+    h->last_launches = 0;
+    // Small batches (the B = 1 drop-in call): inputs and outputs go through ONE pinned staging buffer that mirrors
+    // the arena -- one H2D, the kernels, one D2H, then plain memcpys -- instead of 3 + 13 separate copies.
+    if (B <= 64) {
+        if (off > h->stage_bytes) {
+            if (h->h_stage) cudaFreeHost(h->h_stage);
+            h->h_stage = nullptr, h->stage_bytes = 0;
+            if (fail(h, cudaHostAlloc(&h->h_stage, off, cudaHostAllocDefault), "cudaHostAlloc(stage)")) return ACMPC_ERR_CUDA;
+            h->stage_bytes = off;
+        }
+        char* st = static_cast<char*>(h->h_stage);
+        cudaStream_t s = h->streams[0];
+        memcpy(st + o_paths, paths, nb * 3 * H * 8);
+        if (offsets) memcpy(st + o_off, offsets, nb * 8);
+        if (vmax) memcpy(st + o_vmax, vmax, nb * 8);
+        if (fail(h, cudaMemcpyAsync(base, st, o_ctrl, cudaMemcpyHostToDevice, s), "H2D inputs")) return ACMPC_ERR_CUDA;
+        acmpc_outputs d;
+        memset(&d, 0, sizeof(d));
+        if (out->controls) d.controls = reinterpret_cast<double*>(base + o_ctrl);
+        if (out->prediction) d.prediction = reinterpret_cast<double*>(base + o_pred);
+        if (out->cum_time) d.cum_time = reinterpret_cast<double*>(base + o_ct);
+        if (out->states) d.states = reinterpret_cast<double*>(base + o_st);
+        if (out->v_ref) d.v_ref = reinterpret_cast<double*>(base + o_vr);
+        if (out->cost) d.cost = reinterpret_cast<double*>(base + o_cost);
+        if (out->pri_res) d.pri_res = reinterpret_cast<double*>(base + o_pr);
+        if (out->dua_res) d.dua_res = reinterpret_cast<double*>(base + o_dr);
+        if (out->status) d.status = reinterpret_cast<int32_t*>(base + o_stat);
+        if (out->status_speed) d.status_speed = reinterpret_cast<int32_t*>(base + o_ss);
+        if (out->iters) d.iters = reinterpret_cast<int32_t*>(base + o_it);
+        if (out->rho_updates) d.rho_updates = reinterpret_cast<int32_t*>(base + o_ru);
+        if (out->waypoints) d.waypoints = reinterpret_cast<double*>(base + o_wp);
+        int rc = launch(h, B, reinterpret_cast<const double*>(base + o_paths),
+                        offsets ? reinterpret_cast<const double*>(base + o_off) : nullptr,
+                        vmax ? reinterpret_cast<const double*>(base + o_vmax) : nullptr, is_localised, &d,
+                        reinterpret_cast<double*>(base + o_vr), static_cast<double*>(h->d_warm), 1, s, 0);
+        if (rc != ACMPC_OK) return rc;
+        // the requested fields form a sub-range of the arena's output region: copy from its first to its last byte
+        const size_t o_end = out->waypoints ? off : o_wp;
+        if (fail(h, cudaMemcpyAsync(st + o_ctrl, base + o_ctrl, o_end - o_ctrl, cudaMemcpyDeviceToHost, s), "D2H outputs") ||
+            fail(h, cudaStreamSynchronize(s), "cudaStreamSynchronize"))
+            return ACMPC_ERR_CUDA;
+#define ACMPC_UNSTAGE(field, o, bytes) \
+    if (out->field) memcpy(out->field, st + (o), (bytes));
+        ACMPC_UNSTAGE(controls, o_ctrl, nb * 2 * n * 8)
+        ACMPC_UNSTAGE(prediction, o_pred, nb * 2 * n * 8)
+        ACMPC_UNSTAGE(cum_time, o_ct, nb * n * 8)
+        ACMPC_UNSTAGE(states, o_st, nb * 3 * H * 8)
+        ACMPC_UNSTAGE(v_ref, o_vr, nb * n * 8)
+        ACMPC_UNSTAGE(cost, o_cost, nb * 8)
+        ACMPC_UNSTAGE(pri_res, o_pr, nb * 8)
+        ACMPC_UNSTAGE(dua_res, o_dr, nb * 8)
+        ACMPC_UNSTAGE(status, o_stat, nb * 4)
+        ACMPC_UNSTAGE(status_speed, o_ss, nb * 4)
+        ACMPC_UNSTAGE(iters, o_it, nb * 8)
+        ACMPC_UNSTAGE(rho_updates, o_ru, nb * 8)
+        ACMPC_UNSTAGE(waypoints, o_wp, nb * 7 * n * 8)
+#undef ACMPC_UNSTAGE
+        return ACMPC_OK;
+    }
     // Large batches go through as up to 4 chunks on 4 streams (own ticket queue each), so that the H2D copy of
     // one chunk and the D2H copy of another overlap the kernels of a third.  (Async only from pinned host memory.)
     const int chunks = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
@@ -704,8 +769,6 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
         const int pct[3] = {h->chunk_pct[0], h->chunk_pct[0] + h->chunk_pct[1], h->chunk_pct[0] + h->chunk_pct[1] + h->chunk_pct[2]};
         for (int k = 0; k < 3; ++k) bound[k + 1] = (int)((long long)B * pct[k] / 100) / kWarpsPerCta * kWarpsPerCta;
     }
-    const size_t wstride = warm_bytes_for(H);
-    h->last_launches = 0;
     if (h->d_warm && chunks > 1 &&
         fail(h, cudaStreamSynchronize(h->streams[0]), "cudaStreamSynchronize"))   // the zero-fill of new records
         return ACMPC_ERR_CUDA;
