@@ -521,7 +521,7 @@ struct SpeedQP {
                     double dd = *pd, oo = *po;
                     double lw = oprev * dprev;          // L_{s,s-1}
                     double piv = dd - lw * oprev;
-                    dprev = 1.0 / piv;
+                    dprev = urecip(piv);
                     oprev = oo;
                     AC_LANE0
                     {
@@ -1062,11 +1062,11 @@ struct ControlQP {
                         a22 -= gg[6] * o20 + gg[8] * o22;
                     }
                     // inverse of the SPD 3x3 through LDL'
-                    double d0i = 1.0 / a00;
+                    double d0i = urecip(a00);
                     double l10 = a10 * d0i, l20 = a20 * d0i;
-                    double d1i = 1.0 / (a11 - l10 * a10);
+                    double d1i = urecip(a11 - l10 * a10);
                     double l21 = (a21 - l20 * a10) * d1i;
-                    double d2i = 1.0 / (a22 - l20 * a20 - l21 * (a21 - l20 * a10));
+                    double d2i = urecip(a22 - l20 * a20 - l21 * (a21 - l20 * a10));
                     double w20 = l10 * l21 - l20;   // (L^{-1})_{20}
                     i22 = d2i;
                     i21 = -l21 * d2i;

@@ -240,6 +240,13 @@ AC_DEV VD vrsqrt(const VD& a)
     AC_FOR_LANES r.v[i_] = 1.0 / sqrt(a.v[i_]);
     return r;
 }
+AC_DEV double urecip(double a) { return 1.0 / a; }
+AC_DEV VD vrecip(const VD& a)
+{
+    VD r;
+    AC_FOR_LANES r.v[i_] = 1.0 / a.v[i_];
+    return r;
+}
 AC_DEV double lane_value(const VD& a, int src) { return a.v[src]; }
 
 // warp reductions (same xor-butterfly order as the device build); result is warp-uniform
@@ -374,15 +381,29 @@ AC_DEV VD shfl_up_raw(double a, int d) { return __shfl_up_sync(kFull, a, d); }
 AC_DEV VD shfl_down_raw(double a, int d) { return __shfl_down_sync(kFull, a, d); }
 AC_DEV VD shfl_rot_up1(double a) { return __shfl_sync(kFull, a, ((int)(threadIdx.x & 31) + 31) & 31); }
 AC_DEV bool uni(bool p) { return __any_sync(kFull, p) != 0; }
-// 1/sqrt(a) for a normal, positive a (the equilibration norms are clamped to [1e-4, 1e4]): hardware seed
-// (MUFU.RSQ64H, ~20 bits) + three Newton steps, fully inline -- CUDA's rsqrt() calls a helper per value
+// 1/sqrt(a) and 1/a for a normal a (equilibration norms clamped to [1e-4, 1e4], pivots of SPD blocks, rho):
+// hardware seed (MUFU.RSQ64H / RCP64H, 20 bits) + two Newton steps, fully inline.  tools/seed_probe.cu measured
+// them against the correctly rounded results over [1e-6, 1e6]: 2.7e-16 and 0 (bit-exact) -- CUDA's rsqrt() calls
+// a helper per value and its division carries range checks and a slow path.
+AC_DEV double urecip(double a)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double e = fma(-a, y, 1.0);
+        y = fma(y, e, y);
+    }
+    return y;
+}
+AC_DEV VD vrecip(double a) { return urecip(a); }
 AC_DEV VD vrsqrt(double a)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     const double h = 0.5 * a;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 2; ++k) {
         const double e = fma(-(h * y), y, 0.5);
         y = fma(y, e, y);
     }
