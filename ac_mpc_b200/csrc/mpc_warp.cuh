@@ -1253,8 +1253,15 @@ struct ControlQP {
         pull_prev_rot<C, 3>(ph, cp);
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            VD F[16], G[16], Hc[16];
-            c.tld(T_F, j, F), c.tld(T_G, j, G), c.tld(T_H, j, Hc);
+            VD F[16], G[10], Hc[16];   // of chunk G only s[5] m[3] b22 b31 are needed here (not A)
+            {
+                VD g8[8], g2[2];
+                c.tld(T_F, j, F);
+                tm_ld<8>(c.tm, j * T_STRIDE + T_G, g8), tm_ld<2>(c.tm, j * T_STRIDE + T_G + 8, g2);
+                c.tld(T_H, j, Hc);
+                for (int k = 0; k < 8; ++k) G[k] = g8[k];
+                G[8] = g2[0], G[9] = g2[1];
+            }
             VD e0 = G[GC_M + 0] * xt[j][0] + cp[j][0];
             VD e1 = G[GC_M + 1] * xt[j][1] + cp[j][1];
             VD e2 = G[GC_M + 2] * xt[j][2] + cp[j][2];
