@@ -54,7 +54,7 @@ constexpr int kLevels = 5;                      // Kogge-Stone levels over 32 la
 // TENSOR MEMORY (lane private, 64 doubles = 128 columns per stage; stage (lane, j) of the instance starts
 // at double column j*64 of the lane's row).  Everything the ADMM iteration reads every time lives here and
 // is fetched as 16-double chunks (one tcgen05.ld.32x32b.x32 each):
-//   chunk F  [ 0,16)  rho[5] rinv[5] iv ik rb31 rb22 - -        rewritten by every factorisation
+//   chunk F  [ 0,16)  rho[5] iv ik rb31 rb22 rinv[5] - -        rewritten by every factorisation
 //   chunk G  [16,32)  s[5] m[3] b22 b31 a11 a12 a21 a22 a31 a33 scaled constraint matrix
 //   chunk H  [32,48)  q[2] be[3] lb[5] ub[5] -                  scaled cost / bounds
 //   chunk NS [48,64)  N_s[9] Sigma_s^{-1}[6] -                  block LDL' factor
@@ -67,7 +67,7 @@ enum : int {
     T_STRIDE = 64,
     T_F = 0, T_G = 16, T_H = 32, T_NS = 48,
     // offsets inside the chunks
-    FC_RHO = 0, FC_RINV = 5, FC_IV = 10, FC_IK = 11, FC_RB31 = 12, FC_RB22 = 13,
+    FC_RHO = 0, FC_IV = 5, FC_IK = 6, FC_RB31 = 7, FC_RB22 = 8, FC_RINV = 9,   // [0,9) is what the rhs phase reads
     GC_S = 0, GC_M = 5, GC_B22 = 8, GC_B31 = 9, GC_A = 10,   // a11 a12 a21 a22 a31 a33
     HC_Q = 0, HC_BE = 2, HC_LB = 5, HC_UB = 10,
     NC_N = 0, NC_SI = 9
@@ -1214,8 +1214,14 @@ struct ControlQP {
         VD t[C][3], tn[C][3], ru[C][2], r[C][3], xt[C][3], Aj[C][6];
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
-            VD F[16], G[16], Q[8];   // Q: q[2] be[3] lb[0..2]
-            c.tld(T_F, j, F), c.tld(T_G, j, G);
+            VD F[9], G[16], Q[8];   // F: rho[5] iv ik rb31 rb22 (no rinv here); Q: q[2] be[3] lb[0..2]
+            {
+                VD f8[8], f1[1];
+                tm_ld<8>(c.tm, j * T_STRIDE + T_F, f8), tm_ld<1>(c.tm, j * T_STRIDE + T_F + 8, f1);
+                for (int k = 0; k < 8; ++k) F[k] = f8[k];
+                F[8] = f1[0];
+            }
+            c.tld(T_G, j, G);
             tm_ld<8>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
             const VD z0 = FIRST ? ze[j][0] : Q[HC_BE + 0], z1 = FIRST ? ze[j][1] : Q[HC_BE + 1],
                      z2 = FIRST ? ze[j][2] : Q[HC_BE + 2];
