@@ -173,7 +173,7 @@ __device__ __forceinline__ acmpc::InstanceOut slice_outputs(const acmpc_outputs&
 // small code, high occupancy.  Hands the speed profile to kernel 2 through p.vel ([B,n], = out.v_ref when
 // the caller asked for that field).
 template <int C>
-__global__ void __launch_bounds__(32, 16) acmpc_speed_kernel(const __grid_constant__ KernelParams p)
+__global__ void __launch_bounds__(32, 12) acmpc_speed_kernel(const __grid_constant__ KernelParams p)
 {
     // one warp = one CTA: instances need 25..100+ iterations, and a multi-warp CTA would hold its slots until its
     // slowest warp is done
