@@ -99,7 +99,12 @@ enum : int {
 template <int C>
 struct Layout {
     static constexpr int kWarmDoubles = WR_HEADER + (2 * WR_SPEED_FIELDS + WR_CTRL_FIELDS) * C * 32;
-    static constexpr int kScratch = ((W_FIELDS * C > kLevels * 9) ? W_FIELDS * C : kLevels * 9) * 32;
+    // scan matrices: every element keeps 48 lanes; lanes 32..47 stay zero, so the backward scan reads
+    // "lane + 2^L" without a bounds test and whatever its raw shuffle delivers there is cancelled
+    // (C = 1 keeps 32 lanes and the bounds test: the padding would cost it its third CTA per SM)
+    static constexpr int kScanLanes = (C == 1) ? 32 : 48;
+    static constexpr int kScanDoubles = 9 * kLevels * kScanLanes;
+    static constexpr int kScratch = (W_FIELDS * C * 32 > kScanDoubles) ? W_FIELDS * C * 32 : kScanDoubles;
     static constexpr int kDoubles = K_FIELDS * C * 32 + kScratch;   // shared memory per warp, control phase
     static constexpr int kSpeedDoubles = (2 * C * 32 > 3 * 32 * C) ? 2 * C * 32 : 3 * 32 * C;   // speed phase: raw path / LDL work
     static constexpr int kTmemDoubles = T_STRIDE * C;               // tensor memory per lane
@@ -245,7 +250,8 @@ struct Ctx {
     AC_MEM void st(int f, int j, const VD& v) const { st_lane(col(f, j), v); }
     AC_MEM double* scratch() const { return W; }
     AC_MEM double* wcol(int f, int j) const { return scratch() + (f * C + j) * 32; }
-    AC_MEM double* scan(int lvl, int e) const { return scratch() + (lvl * 9 + e) * 32; }
+    // element e of the level-L scan matrices: scan(L, e)[lane], lanes 0 .. 47
+    AC_MEM double* scan(int lvl, int e) const { return scratch() + (lvl * 9 + e) * Layout<C>::kScanLanes; }
     AC_MEM VI stage(int j) const { return lane * C + j; }
     // tensor-memory chunk `ch` (T_F, T_G, T_H, T_NS) of own stage j
     AC_MEM void tld(int ch, int j, VD (&o)[16]) const { tm_ld<16>(tm, j * T_STRIDE + ch, o); }
@@ -1108,6 +1114,8 @@ struct ControlQP {
             VD U[9], T[9];
             for (int e = 0; e < 9; ++e) {
                 st_lane(c.scan(L, e), F[e]);
+                // re-zero the 16 lanes past lane 31 (the factorisation's work arrays lived here)
+                if (Layout<C>::kScanLanes > 32) st_idx_if(vi_lt(c.lane, 16), c.scan(L, e), c.lane + 32, VD(0.0));
                 U[e] = shfl_up0(F[e], 1 << L);
             }
             for (int r = 0; r < 3; ++r)
@@ -1136,10 +1144,10 @@ struct ControlQP {
         {
             const double* sp = c.scan(0, 0);
             AC_NOUNROLL
-            for (int L = 0; L < kLevels; ++L, sp += 9 * 32) {
+            for (int L = 0; L < kLevels; ++L, sp += 9 * Layout<C>::kScanLanes) {
                 VD U[3];
                 for (int e = 0; e < 3; ++e) U[e] = shfl_up_raw(Y[e], 1 << L);
-                for (int e = 0; e < 9; ++e) M[e] = ld_lane(sp + e * 32);
+                for (int e = 0; e < 9; ++e) M[e] = ld_lane(sp + e * Layout<C>::kScanLanes);
                 mv_acc9(M, U, Y);
             }
         }
@@ -1185,10 +1193,16 @@ struct ControlQP {
         {
             const double* sp = c.scan(0, 0);
             AC_NOUNROLL
-            for (int L = 0; L < kLevels; ++L, sp += 9 * 32) {
+            for (int L = 0; L < kLevels; ++L, sp += 9 * Layout<C>::kScanLanes) {
                 VD U[3];
-                for (int e = 0; e < 3; ++e) U[e] = shfl_down0(Z[e], 1 << L);
-                for (int e = 0; e < 9; ++e) M[e] = ld_lane_at(sp + e * 32, 1 << L);
+                if (Layout<C>::kScanLanes > 32) {
+                    for (int e = 0; e < 3; ++e) U[e] = shfl_down_raw(Z[e], 1 << L);
+                    const double* spl = sp + (1 << L);   // lane + 2^L: zeros past lane 31
+                    for (int e = 0; e < 9; ++e) M[e] = ld_lane(spl + e * Layout<C>::kScanLanes);
+                } else {
+                    for (int e = 0; e < 3; ++e) U[e] = shfl_down0(Z[e], 1 << L);
+                    for (int e = 0; e < 9; ++e) M[e] = ld_lane_at(sp + e * Layout<C>::kScanLanes, 1 << L);
+                }
                 mtv_acc9(M, U, Z);
             }
         }
