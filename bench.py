@@ -220,12 +220,21 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     d_vmax = torch.from_numpy(vmax).to(dev)
     packed, views = mpc.alloc_device_outputs(B, BENCH_FIELDS)
     gathered = torch.empty(world * packed.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
+    # the one collective of the path: the packed results of every rank end up on rank 0 ("gather", the default:
+    # rank 0 is where the caller lives) or on every rank ("all_gather")
+    slots = list(gathered.view(world, -1).unbind(0)) if (world > 1 and rank == 0) else None
+
+    def collect():
+        if args.collective == "gather":
+            dist.gather(packed, slots, dst=0)
+        else:
+            dist.all_gather_into_tensor(gathered, packed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def step():
         mpc.solve_device(d_paths, None, d_vmax, False, out=views)
         if world > 1:   # the one collective of the path: final gather of the packed results over NVLink
-            dist.all_gather_into_tensor(gathered, packed)
+            collect()
 
     for _ in range(max(W, 3)):
         step()
@@ -246,7 +255,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         mpc.solve_device(d_paths, None, d_vmax, False, out=views)
         kev[i][1].record()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, packed)
+            collect()
         ev[i][1].record()
     torch.cuda.synchronize()
     per_kernel = mpc.collect_kernel_ms()
@@ -339,7 +348,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                                "(BASELINE configs[1]), cold start per instance",
                    "track": args.track, "horizon": H, "batch_per_gpu": B, "global_batch": world * B,
                    "l2": "flushed between timed steps (256 MiB fill outside the events)",
-                   "parallelism": f"instances sharded over {world} GPU(s), one final NCCL all-gather" if world > 1
+                   "parallelism": f"instances sharded over {world} GPU(s), one final NCCL {args.collective}" if world > 1
                    else "single GPU", "osqp": "eps_abs=eps_rel=1e-3, check 25, adaptive rho interval 50"},
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * bin_,
                 "d2h_bytes_per_step": B * bout, "api": "SpatialMPC.get_control_batch -> acmpc_solve_batch_host"},
@@ -380,6 +389,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU per step")
+    ap.add_argument("--collective", default="gather", choices=["gather", "all_gather"],
+                    help="N > 1: where the packed results go at the end of a step (rank 0 / every rank)")
     ap.add_argument("--track", default="monza")
     ap.add_argument("--horizon", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall-clock budget of the cpu_baseline leg")
