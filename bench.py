@@ -9,7 +9,7 @@ A "step" is one pass of the hot path (SpatialMPC.get_control: waypoints + speed-
 linearise/assemble + control QP + unpack/rollout/cost) over one batch of synthetic instances:
 BASELINE.json configs[1] = Monza racing block (H = 50), 4096 perturbed initial states per GPU.
 At N > 1 every rank solves its own 4096-instance shard (weak scaling, no data-path collective) and the
-step ends with the single NCCL all-gather of the packed outputs.
+step ends with the single NCCL collective that brings the packed outputs to rank 0 (--collective all_gather: to every rank).
 
 One JSON line on stdout (rank 0).  `value` = device-timed throughput with inputs resident in HBM;
 `e2e` = the same metric through the reference-facing API (SpatialMPC.get_control_batch -> C ABI host
