@@ -287,6 +287,7 @@ struct acmpc_handle {
     size_t order_cap[4];     // instances each can hold
     int order_parity[4];     // counter set of the last launch
     int order_on;            // ACMPC_ORDER=0 switches the ordering off
+    int order_min;           // smallest batch that is ordered (ACMPC_ORDER_MIN, default 1024)
     int chunk_pct[3];        // share of the first three chunks of a 4-chunk host call, in percent
     void* d_warm;            // warm-start records of the host entry point (keep_warm)
     int warm_B;
@@ -398,7 +399,7 @@ size_t speed_smem_bytes_for(int H)
 // (re)allocate the order buffer of chunk stream `qi` for B instances; synchronous, only when it has to grow
 bool ensure_order(acmpc_handle* h, int qi, int B)
 {
-    if (!h->order_on || B < 1024 || (size_t)B <= h->order_cap[qi]) return true;
+    if (!h->order_on || B < h->order_min || (size_t)B <= h->order_cap[qi]) return true;
     if (h->d_order[qi]) {
         if (fail(h, cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return false;
         cudaFree(h->d_order[qi]);
@@ -442,7 +443,7 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     if (p.persistent) h->queue_pos[qi] += (uint32_t)B;   // every solved instance draws one ticket
     // longest-first order for batches that run several rounds of the device (see KernelParams::order)
     p.order = nullptr;
-    if (h->order_on && B >= 1024 && h->d_order[qi] && (size_t)B <= h->order_cap[qi]) {
+    if (h->order_on && B >= h->order_min && h->d_order[qi] && (size_t)B <= h->order_cap[qi]) {
         p.order = h->d_order[qi];
         p.order_set = (h->order_parity[qi] ^= 1);
         if (d_vmax) {
@@ -530,6 +531,9 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
     {
         const char* e = getenv("ACMPC_ORDER");
         h->order_on = (e && e[0] == '0') ? 0 : 1;
+        const char* m = getenv("ACMPC_ORDER_MIN");
+        h->order_min = m ? atoi(m) : 1024;
+        if (h->order_min < 1) h->order_min = 1;
         h->chunk_pct[0] = 25, h->chunk_pct[1] = 25, h->chunk_pct[2] = 25;
         const char* c = getenv("ACMPC_CHUNKS");   // e.g. "25,25,25" (experiments)
         if (c) sscanf(c, "%d,%d,%d", &h->chunk_pct[0], &h->chunk_pct[1], &h->chunk_pct[2]);
@@ -643,6 +647,9 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
     {
         const char* e = getenv("ACMPC_ORDER");
         h->order_on = (e && e[0] == '0') ? 0 : 1;
+        const char* m = getenv("ACMPC_ORDER_MIN");
+        h->order_min = m ? atoi(m) : 1024;
+        if (h->order_min < 1) h->order_min = 1;
         h->chunk_pct[0] = 25, h->chunk_pct[1] = 25, h->chunk_pct[2] = 25;
         const char* c = getenv("ACMPC_CHUNKS");   // e.g. "25,25,25" (experiments)
         if (c) sscanf(c, "%d,%d,%d", &h->chunk_pct[0], &h->chunk_pct[1], &h->chunk_pct[2]);
