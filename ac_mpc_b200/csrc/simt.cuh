@@ -205,12 +205,6 @@ AC_DEV VD shfl_down0(const VD& a, int d)
     AC_FOR_LANES r.v[i_] = (i_ + d < 32) ? a.v[i_ + d] : 0.0;
     return r;
 }
-AC_DEV VD shfl_idx(const VD& a, int src)
-{
-    VD r;
-    AC_FOR_LANES r.v[i_] = a.v[src];
-    return r;
-}
 // "raw" shuffles: an out-of-range source delivers the lane's OWN value (the hardware behaviour); callers
 // multiply the result by a coefficient that is zero on those lanes
 AC_DEV VD shfl_up_raw(const VD& a, int d)
@@ -303,7 +297,6 @@ AC_DEV VD ld_lane_at(const double* base, int off)
     AC_FOR_LANES r.v[i_] = base[(i_ + off < 32) ? i_ + off : 31];
     return r;
 }
-AC_DEV VB vb_not(const VB& a) { return !a; }
 
 // ---- tensor memory (TMEM) as a lane-private scratchpad: the emulation models it as [double column][lane]
 struct Tm {
@@ -376,7 +369,6 @@ AC_DEV VD shfl_down0(double a, int d)
     double t = __shfl_down_sync(kFull, a, d);
     return ((int)(threadIdx.x & 31) + d < 32) ? t : 0.0;
 }
-AC_DEV VD shfl_idx(double a, int src) { return __shfl_sync(kFull, a, src); }
 AC_DEV VD shfl_up_raw(double a, int d) { return __shfl_up_sync(kFull, a, d); }
 AC_DEV VD shfl_down_raw(double a, int d) { return __shfl_down_sync(kFull, a, d); }
 AC_DEV VD shfl_rot_up1(double a) { return __shfl_sync(kFull, a, ((int)(threadIdx.x & 31) + 31) & 31); }
@@ -440,7 +432,6 @@ AC_DEV VD ld_lane_at(const double* base, int off)
     int i = (int)(threadIdx.x & 31) + off;
     return base[i < 32 ? i : 31];
 }
-AC_DEV VB vb_not(bool a) { return !a; }
 
 // ---- tensor memory (TMEM) as a lane-private scratchpad.  One double = two 32-bit columns of the lane's
 // row; `a` = TMEM address (lane quarter of the warp << 16 | first column of the instance).  Every load is
