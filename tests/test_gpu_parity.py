@@ -351,3 +351,18 @@ def test_track_narrower_than_the_car_is_rejected_like_osqp_does():
     assert np.all(got["status"] == -10) and np.all(want["status"] == -10)
     assert np.array_equal(got["iters"], want["iters"]) and np.array_equal(got["status_speed"], want["status_speed"])
     np.testing.assert_allclose(got["v_ref"], want["v_ref"], rtol=0, atol=TOL)
+
+
+def test_localised_batch_with_offsets_through_the_ordered_pipelined_path():
+    """2560 instances: large enough for the longest-first order kernel and for the host entry point's 4-chunk
+    pipeline, with is_localised=True, per-instance offsets and v_max, against the oracle."""
+    import _golden
+
+    kw = _golden.racing_kwargs("silverstone")
+    B = 2560
+    paths, vmax = tracks.perturbed_batch("silverstone", B, seed=31)
+    offs = np.random.default_rng(8).uniform(-0.6, 0.6, B)
+    got = _solver(**kw).solve_host(paths, offs, vmax, True)
+    want = port.solve_batch(port.default_config(**kw), paths, offs, vmax, True, nthreads=16)
+    _assert_equals_oracle(got, want)
+    np.testing.assert_allclose(got["waypoints"], want["waypoints"], rtol=0, atol=TOL)
