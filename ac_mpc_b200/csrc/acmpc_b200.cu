@@ -288,7 +288,6 @@ struct acmpc_handle {
     int order_parity[4];     // counter set of the last launch
     int order_on;            // ACMPC_ORDER=0 switches the ordering off
     int order_min;           // smallest batch that is ordered (ACMPC_ORDER_MIN, default 1024)
-    int chunk_pct[3];        // share of the first three chunks of a 4-chunk host call, in percent
     void* d_warm;            // warm-start records of the host entry point (keep_warm)
     int warm_B;
     void* d_vel;             // speed-profile hand-over buffer of the device entry point (when v_ref is not requested)
@@ -534,9 +533,6 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
         const char* m = getenv("ACMPC_ORDER_MIN");
         h->order_min = m ? atoi(m) : 1024;
         if (h->order_min < 1) h->order_min = 1;
-        h->chunk_pct[0] = 25, h->chunk_pct[1] = 25, h->chunk_pct[2] = 25;
-        const char* c = getenv("ACMPC_CHUNKS");   // e.g. "25,25,25" (experiments)
-        if (c) sscanf(c, "%d,%d,%d", &h->chunk_pct[0], &h->chunk_pct[1], &h->chunk_pct[2]);
     }
     h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
     {
@@ -650,9 +646,6 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
         const char* m = getenv("ACMPC_ORDER_MIN");
         h->order_min = m ? atoi(m) : 1024;
         if (h->order_min < 1) h->order_min = 1;
-        h->chunk_pct[0] = 25, h->chunk_pct[1] = 25, h->chunk_pct[2] = 25;
-        const char* c = getenv("ACMPC_CHUNKS");   // e.g. "25,25,25" (experiments)
-        if (c) sscanf(c, "%d,%d,%d", &h->chunk_pct[0], &h->chunk_pct[1], &h->chunk_pct[2]);
     }
     h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
             if (fail(h, cudaMalloc(&h->d_vel, need), "cudaMalloc(vel)")) return ACMPC_ERR_CUDA;
@@ -768,24 +761,22 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
     }
     // Large batches go through as up to 4 chunks on 4 streams (own ticket queue each), so that the H2D copy of
     // one chunk and the D2H copy of another overlap the kernels of a third.  (Async only from pinned host memory.)
-    const int chunks = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
-    // chunk boundaries (equal quarters measured best; ACMPC_CHUNKS=a,b,c overrides the first three shares)
-    int bound[5] = {0, B, B, B, B};
-    if (chunks == 2) bound[1] = B / 2 / kWarpsPerCta * kWarpsPerCta;
-    if (chunks == 4) {
-        const int pct[3] = {h->chunk_pct[0], h->chunk_pct[0] + h->chunk_pct[1], h->chunk_pct[0] + h->chunk_pct[1] + h->chunk_pct[2]};
-        for (int k = 0; k < 3; ++k) bound[k + 1] = (int)((long long)B * pct[k] / 100) / kWarpsPerCta * kWarpsPerCta;
-    }
+    // 2 chunks from 512 instances, 4 from 2048, then chunks of at most 16384 instances dealt round-robin to the 4
+    // streams (a 1 M-instance sweep would otherwise wait for a 300 MB H2D before its first kernel)
+    int chunks = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
+    if (B > 4 * 16384) chunks = (B + 16383) / 16384;
+    const int per = ((B + chunks - 1) / chunks + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
     if (h->d_warm && chunks > 1 &&
         fail(h, cudaStreamSynchronize(h->streams[0]), "cudaStreamSynchronize"))   // the zero-fill of new records
         return ACMPC_ERR_CUDA;
     for (int k = 0; k < chunks; ++k) {
-        const int c0 = bound[k];
-        const int cb = bound[k + 1] - c0;
+        const int c0 = k * per;
+        const int cb = (c0 + per <= B) ? per : B - c0;
         if (cb <= 0) break;
-        cudaStream_t s = h->streams[k];
+        const int qi = k & 3;
+        cudaStream_t s = h->streams[qi];
         const size_t z = (size_t)c0, nbk = (size_t)cb;
-        if (!ensure_order(h, k, cb)) return ACMPC_ERR_CUDA;
+        if (!ensure_order(h, qi, per)) return ACMPC_ERR_CUDA;
         if (fail(h, cudaMemcpyAsync(base + o_paths + z * 3 * H * 8, paths + z * 3 * H, nbk * 3 * H * 8,
                                     cudaMemcpyHostToDevice, s), "H2D paths"))
             return ACMPC_ERR_CUDA;
@@ -814,7 +805,7 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
                         offsets ? reinterpret_cast<const double*>(base + o_off) + z : nullptr,
                         vmax ? reinterpret_cast<const double*>(base + o_vmax) + z : nullptr, is_localised, &d,
                         reinterpret_cast<double*>(base + o_vr) + z * n,
-                        h->d_warm ? reinterpret_cast<double*>(static_cast<char*>(h->d_warm) + z * wstride) : nullptr, 1, s, k);
+                        h->d_warm ? reinterpret_cast<double*>(static_cast<char*>(h->d_warm) + z * wstride) : nullptr, 1, s, qi);
         if (rc != ACMPC_OK) return rc;
 #define ACMPC_D2H(field, per_inst, type)                                                                        \
     if (out->field && fail(h, cudaMemcpyAsync(out->field + z * (per_inst), d.field, nbk * (per_inst) * sizeof(type), \
@@ -835,7 +826,7 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
         ACMPC_D2H(waypoints, 7 * n, double)
 #undef ACMPC_D2H
     }
-    for (int k = 0; k < chunks; ++k)
+    for (int k = 0; k < 4; ++k)
         if (fail(h, cudaStreamSynchronize(h->streams[k]), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
 }

@@ -138,7 +138,7 @@ int32_t acmpc_solve_batch_host(acmpc_handle *h, int32_t B, const double *paths,
 
 /* Counters of the last call: kernel launches issued (per chunk: speed-profile kernel + control kernel, plus the
  * small ordering kernel for batches of 1024+ with per-instance v_max; the host entry point splits batches of
- * 512+ / 2048+ into 2 / 4 chunks), dynamic shared memory per CTA of the control kernel, threads per CTA,
+ * 512+ / 2048+ into 2 / 4 chunks and larger ones into chunks of at most 16384 instances), dynamic shared memory per CTA of the control kernel, threads per CTA,
  * instances per CTA. */
 int32_t acmpc_last_launch_info(const acmpc_handle *h, int32_t *n_launches, int32_t *smem_bytes,
                                int32_t *threads_per_cta, int32_t *instances_per_cta);
