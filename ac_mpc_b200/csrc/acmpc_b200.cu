@@ -1,11 +1,15 @@
-// acmpc_b200.cu -- sm_100a kernel + C ABI (include/acmpc_b200.h) of the batched MPC step.
+// acmpc_b200.cu -- sm_100a kernels + C ABI (include/acmpc_b200.h) of the batched MPC step.
 //
-// One warp owns one problem instance (four warps = four instances per CTA); its (H,3) reference-path
-// slice is staged into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier), everything else
-// (waypoints, both QPs, ADMM iterates, factorisations) stays in that warp's registers, its quarter of the
-// CTA's TENSOR MEMORY allocation (used as a lane-private FP64 scratchpad through tcgen05.ld/st) and its
-// slice of shared memory until the results are written back.  The per-instance algorithm is in mpc_warp.cuh; the kernel is
-// instantiated for C = ceil(H/32) = 1..4 horizon stages per lane.
+// One warp owns one problem instance.  A step is two kernels (three for batches of 1024+ instances):
+//   acmpc_order_kernel     bins the instances by their live v_max (longest-first scheduling)
+//   acmpc_speed_kernel<C>  waypoints + speed-profile QP, registers only, one warp per CTA
+//   acmpc_control_kernel<C> control QP + unpack + rollout + cost; four warps = four instances per CTA; the warp's
+//                          (H,3) reference-path slice is staged into shared memory with a TMA bulk copy
+//                          (cp.async.bulk + mbarrier), the ADMM iterates stay in registers, the scaled problem and
+//                          its factor in the warp's quarter of the CTA's TENSOR MEMORY allocation (a lane-private
+//                          FP64 scratchpad through tcgen05.ld/st), the cross-lane data in its slice of shared memory
+// The per-instance algorithm is in mpc_warp.cuh; the kernels are instantiated for C = ceil(H/32) = 1..4 horizon
+// stages per lane.
 //
 // There is NO CPU path in this library: acmpc_create fails with ACMPC_ERR_NO_DEVICE without a GPU.
 #include <cuda_runtime.h>
@@ -437,7 +441,6 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     const int resident = h->sm_count * h->ctas_per_sm;
     p.persistent = h->persistent;
     if (p.persistent && ctas > resident) ctas = resident;
-    if (getenv("ACMPC_DEBUG")) fprintf(stderr, "acmpc launch: B=%d ctas=%d ctas_per_sm=%d sms=%d smem=%zu\n", B, ctas, h->ctas_per_sm, h->sm_count, smem);
     p.queue = h->d_queue + qi, p.queue_base = h->queue_pos[qi], p.warps_launched = (uint32_t)(ctas * kWarpsPerCta);
     if (p.persistent) h->queue_pos[qi] += (uint32_t)B;   // every solved instance draws one ticket
     // longest-first order for batches that run several rounds of the device (see KernelParams::order)
