@@ -403,14 +403,15 @@ AC_DEV VD vrsqrt(double a)
 }
 AC_DEV double lane_value(double a, int src) { return __shfl_sync(kFull, a, src); }
 
+// max over the warp of NON-NEGATIVE values (norms, magnitudes): two 32-bit REDUX instead of a five-level
+// 64-bit shuffle butterfly -- for non-negative doubles the (high word, low word) order is the numeric order
 AC_DEV double wmax(double v)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double t = __shfl_xor_sync(kFull, v, o);
-        v = v > t ? v : t;
-    }
-    return v;
+    const int hi = __double2hiint(v);   // signed: a -0.0 loses against everything instead of winning
+    const unsigned lo = (unsigned)__double2loint(v);
+    const int hmax = __reduce_max_sync(kFull, hi);
+    const unsigned lmax = __reduce_max_sync(kFull, hi == hmax ? lo : 0u);
+    return __hiloint2double(hmax, (int)lmax);
 }
 AC_DEV double wsum(double v)
 {
