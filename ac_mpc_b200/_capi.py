@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libacmpc_b200.so")
 _SOURCES = [os.path.join(CSRC, "acmpc_b200.cu"), os.path.join(CSRC, "mpc_warp.cuh"), os.path.join(CSRC, "simt.cuh"),
+            os.path.join(CSRC, "map_profile.cuh"),
             os.path.join(os.path.dirname(_HERE), "include", "acmpc_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -24,6 +25,8 @@ EXPORTED = [
     "acmpc_abi_version", "acmpc_default_config", "acmpc_create", "acmpc_destroy", "acmpc_last_error",
     "acmpc_warm_stride", "acmpc_solve_batch_device", "acmpc_solve_batch_host", "acmpc_last_launch_info",
     "acmpc_fp64_peak_tflops", "acmpc_set_profiling", "acmpc_collect_kernel_ms",
+    "acmpc_construct_waypoints_host", "acmpc_map_speed_profile_host", "acmpc_track_speed_profile_host",
+    "acmpc_reference_speeds_host",
 ]
 
 RC_NAMES = {0: "ACMPC_OK", 1: "ACMPC_ERR_INVALID", 2: "ACMPC_ERR_CUDA", 3: "ACMPC_ERR_NO_DEVICE"}
@@ -52,6 +55,14 @@ class Config(C.Structure):
         ("scaling", C.c_int32), ("check_termination", C.c_int32),
         ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32),
     ]
+
+
+class MapInfo(C.Structure):
+    """`acmpc_map_info`."""
+
+    _fields_ = [("status", C.c_int32), ("iters", C.c_int32), ("rho_updates", C.c_int32), ("ctas", C.c_int32),
+                ("pri_res", C.c_double), ("dua_res", C.c_double), ("obj_val", C.c_double), ("rho", C.c_double),
+                ("kernel_ms", C.c_double)]
 
 
 OUTPUT_FIELDS = ["controls", "prediction", "cum_time", "states", "v_ref", "cost", "pri_res", "dua_res",
@@ -134,6 +145,16 @@ def load() -> C.CDLL:
     L.acmpc_set_profiling.restype = C.c_int32
     L.acmpc_collect_kernel_ms.argtypes = [vp, dp, dp, C.POINTER(C.c_int32)]
     L.acmpc_collect_kernel_ms.restype = C.c_int32
+    L.acmpc_construct_waypoints_host.argtypes = [vp, C.c_int32, dp, dp]
+    L.acmpc_construct_waypoints_host.restype = C.c_int32
+    L.acmpc_map_speed_profile_host.argtypes = [vp, C.c_int32, dp, C.c_double, C.c_double, C.c_double, C.c_int32, dp,
+                                               C.POINTER(MapInfo)]
+    L.acmpc_map_speed_profile_host.restype = C.c_int32
+    L.acmpc_track_speed_profile_host.argtypes = [vp, C.c_int32, dp, C.c_double, C.c_double, C.c_double, C.c_int32,
+                                                 dp, dp, C.POINTER(MapInfo)]
+    L.acmpc_track_speed_profile_host.restype = C.c_int32
+    L.acmpc_reference_speeds_host.argtypes = [vp, C.c_int32, dp, C.c_int32, C.c_int32, dp, dp]
+    L.acmpc_reference_speeds_host.restype = C.c_int32
     _lib = L
     return L
 

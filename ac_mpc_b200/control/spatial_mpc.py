@@ -113,11 +113,25 @@ class SpatialMPC:
             logger.warning(f"Infeasible problem! Failed {self.infeasibility_counter} time(s).")
             self.infeasibility_counter += 1
 
-    # -- entry points of the whole-track profile: not built yet -----
-    def compute_map_speed_profile(self, reference_path, ay_max: float, a_min: float):
-        raise NotImplementedError(
-            "whole-track speed profile (spatial_mpc.py:60-87) is a 'next' row of the scope table; "
-            "it is not implemented on the GPU yet and there is deliberately no CPU fallback")
+    # -- the whole-track profile (spatial_mpc.py:60-87, :125-154) ------
+    def construct_waypoints(self, waypoint_coordinates) -> ReferencePath:
+        """(M,3) array of (x, y, width) -> ReferencePath of M-1 waypoints (spatial_mpc.py:125-154), on the GPU."""
+        rows = self._batched().construct_waypoints(np.asarray(waypoint_coordinates, dtype=np.float64))
+        return ReferencePath(rows.shape[1], rows)
+
+    def compute_map_speed_profile(self, reference_path: ReferencePath, ay_max: float, a_min: float) -> ReferencePath:
+        """One cooperative launch solves the whole-track QP (max_iter = 40000).  Velocities are assigned only when
+        OSQP's status is "solved" (spatial_mpc.py:115-123), otherwise a warning is logged."""
+        rows = reference_path.as_array()
+        x, info = self._batched().map_speed_profile(rows, float(self.speed_profile_constraints["v_max"]), ay_max,
+                                                    a_min, MAX_SOLVER_ITERATIONS_MAP)
+        self.last_map_info = info
+        if info["status"] == 1:
+            self.speed_profile = x
+        else:
+            failed = np.hstack([reference_path.xs, reference_path.ys])
+            logger.warning("Infeasible problem! reference path:\n" + f"{failed}")
+        return reference_path
 
     def compute_speed_profile(self, reference_path, is_localised: bool = False, end_vel=None):
         raise NotImplementedError(

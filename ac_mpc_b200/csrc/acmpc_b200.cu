@@ -22,6 +22,7 @@
 #include <string>
 
 #include "mpc_warp.cuh"
+#include "map_profile.cuh"
 
 namespace {
 
@@ -917,6 +918,181 @@ int32_t acmpc_fp64_peak_tflops(int32_t device, double* tflops)
     const double flops = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
     *tflops = flops / (best * 1e-3) / 1e12;
     return ACMPC_OK;
+}
+
+}  // extern "C"
+
+// ---- whole-track speed profile (map_profile.cuh) -------------------------------------------------------------
+namespace {
+
+// one launch of the map kernel.  h_track [M,3] or nullptr; h_way [7,n] in/out; do_solve 0 = waypoints only
+int32_t run_map(acmpc_handle* h, int M, int n, const double* h_track, double* h_way, int do_solve, double v_max,
+                double ay_max, double a_min, int max_iter, double* h_solution, acmpc_map_info* info)
+{
+    using namespace acmpc::mapqp;
+    if (!h || !h_way || n < 2 || (h_track && M != n + 1)) return ACMPC_ERR_INVALID;
+    const int ctas = (n + kThreads - 1) / kThreads;
+    if (ctas > h->sm_count || ctas > kMaxCtas) {
+        h->err = "track too long for one cooperative launch (n > 512 * SM count)";
+        return ACMPC_ERR_INVALID;
+    }
+    if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    MapParams p;
+    memset(&p, 0, sizeof(p));
+    p.cfg = h->cfg;
+    p.cfg.v_max = v_max, p.cfg.ay_max = ay_max, p.cfg.a_min = a_min;
+    p.cfg.max_iter = max_iter > 0 ? max_iter : ACMPC_MAP_MAX_ITER;
+    p.cfg.has_end_velocity = 0;   // compute_map_speed_profile passes no end velocity (spatial_mpc.py:71)
+    p.M = M, p.n = n, p.do_solve = do_solve;
+    const size_t way_b = (size_t)7 * n * 8, trk_b = h_track ? (size_t)3 * M * 8 : 0, k_b = (size_t)ctas * kThreads * 8;
+    const size_t slots_b = 2 * (kMaxCtas + 1) * sizeof(double2), halo_b = (size_t)2 * 2 * kMaxCtas * kWarps * 8,
+                 red_b = (size_t)2 * kMaxCtas * kRed * 8;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t total = up(way_b) + up(trk_b) + up((size_t)n * 8) + 2 * up(k_b) + up(slots_b) + up(halo_b) +
+                         up(red_b) + up(64) + 256;
+    char* base = nullptr;
+    if (fail(h, cudaMalloc((void**)&base, total), "cudaMalloc(map profile)")) return ACMPC_ERR_CUDA;
+    char* q = base;
+    auto take = [&](size_t b) { char* r = q; q += up(b); return r; };
+    p.waypoints = (double*)take(way_b);
+    double* d_track = (double*)take(trk_b);
+    p.track = h_track ? d_track : nullptr;
+    p.solution = (double*)take((size_t)n * 8);
+    p.kd = (double*)take(k_b), p.ko = (double*)take(k_b);
+    p.slots = (double2*)take(slots_b);
+    p.halo = (double*)take(halo_b);
+    p.red = (double*)take(red_b);
+    p.info = (double*)take(64);
+    p.counter = (unsigned*)take(256);
+    cudaStream_t st = h->stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int32_t rc = ACMPC_OK;
+    double h_info[8] = {0};
+    float ms = 0.f;
+    void* args[] = {(void*)&p};
+    if (fail(h, cudaMemsetAsync(base, 0, total, st), "cudaMemsetAsync(map profile)") ||
+        (h_track && fail(h, cudaMemcpyAsync(d_track, h_track, trk_b, cudaMemcpyHostToDevice, st), "H2D(track)")) ||
+        (!h_track && fail(h, cudaMemcpyAsync(p.waypoints, h_way, way_b, cudaMemcpyHostToDevice, st), "H2D(waypoints)")) ||
+        fail(h, cudaEventCreate(&e0), "cudaEventCreate") || fail(h, cudaEventCreate(&e1), "cudaEventCreate") ||
+        fail(h, cudaEventRecord(e0, st), "cudaEventRecord") ||
+        fail(h, cudaLaunchCooperativeKernel((const void*)acmpc_map_profile_kernel, dim3(ctas), dim3(kThreads), args, 0, st),
+             "cudaLaunchCooperativeKernel(map profile)") ||
+        fail(h, cudaEventRecord(e1, st), "cudaEventRecord") ||
+        fail(h, cudaMemcpyAsync(h_way, p.waypoints, way_b, cudaMemcpyDeviceToHost, st), "D2H(waypoints)") ||
+        (h_solution && do_solve &&
+         fail(h, cudaMemcpyAsync(h_solution, p.solution, (size_t)n * 8, cudaMemcpyDeviceToHost, st), "D2H(solution)")) ||
+        fail(h, cudaMemcpyAsync(h_info, p.info, 64, cudaMemcpyDeviceToHost, st), "D2H(info)") ||
+        fail(h, cudaStreamSynchronize(st), "map profile kernel") ||
+        fail(h, cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime"))
+        rc = ACMPC_ERR_CUDA;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(base);
+    if (rc == ACMPC_OK && h_info[7] != 0.0) {
+        h->err = "map profile kernel: grid barrier timed out";
+        rc = ACMPC_ERR_CUDA;
+    }
+    if (rc == ACMPC_OK) {
+        h->last_launches = 1, h->last_smem = (int)sizeof(Shared), h->last_threads = kThreads, h->last_ipc = 1;
+        if (info) {
+            info->status = do_solve ? (int32_t)h_info[0] : ACMPC_UNSOLVED;
+            info->iters = (int32_t)h_info[1], info->rho_updates = (int32_t)h_info[2], info->ctas = ctas;
+            info->pri_res = h_info[3], info->dua_res = h_info[4], info->obj_val = h_info[5], info->rho = h_info[6];
+            info->kernel_ms = ms;
+        }
+    }
+    return rc;
+}
+
+// weights of the least-squares cubic over x = -10 .. 10 evaluated at x = e  (scipy.signal.savgol_coeffs /
+// the polynomial fit of mode "interp")
+void savgol_weights(double e, double* w)
+{
+    using namespace acmpc::mapqp;
+    long double G[4][5];
+    for (int a = 0; a < 4; ++a) {
+        for (int b = 0; b < 4; ++b) {
+            long double t = 0;
+            for (int k = -kSgHalf; k <= kSgHalf; ++k) t += powl((long double)k, a + b);
+            G[a][b] = t;
+        }
+        G[a][4] = powl((long double)e, a);
+    }
+    // solve G c = (e^a): weights w_k = sum_b c_b k^b
+    for (int i = 0; i < 4; ++i) {
+        int piv = i;
+        for (int r = i + 1; r < 4; ++r)
+            if (fabsl(G[r][i]) > fabsl(G[piv][i])) piv = r;
+        for (int c = 0; c < 5; ++c) {
+            long double t = G[i][c];
+            G[i][c] = G[piv][c], G[piv][c] = t;
+        }
+        for (int r = 0; r < 4; ++r) {
+            if (r == i) continue;
+            const long double f = G[r][i] / G[i][i];
+            for (int c = i; c < 5; ++c) G[r][c] -= f * G[i][c];
+        }
+    }
+    for (int k = -kSgHalf; k <= kSgHalf; ++k) {
+        long double t = 0;
+        for (int b = 0; b < 4; ++b) t += (G[b][4] / G[b][b]) * powl((long double)k, b);
+        w[k + kSgHalf] = (double)t;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t acmpc_construct_waypoints_host(acmpc_handle* h, int32_t M, const double* track, double* waypoints)
+{
+    if (!track) return ACMPC_ERR_INVALID;
+    return run_map(h, M, M - 1, track, waypoints, 0, 0.0, 0.0, 0.0, 0, nullptr, nullptr);
+}
+
+int32_t acmpc_map_speed_profile_host(acmpc_handle* h, int32_t n, double* waypoints, double v_max, double ay_max,
+                                     double a_min, int32_t max_iter, double* solution, acmpc_map_info* info)
+{
+    return run_map(h, n + 1, n, nullptr, waypoints, 1, v_max, ay_max, a_min, max_iter, solution, info);
+}
+
+int32_t acmpc_track_speed_profile_host(acmpc_handle* h, int32_t M, const double* track, double v_max, double ay_max,
+                                       double a_min, int32_t max_iter, double* waypoints, double* solution,
+                                       acmpc_map_info* info)
+{
+    if (!track) return ACMPC_ERR_INVALID;
+    return run_map(h, M, M - 1, track, waypoints, 1, v_max, ay_max, a_min, max_iter, solution, info);
+}
+
+int32_t acmpc_reference_speeds_host(acmpc_handle* h, int32_t n, const double* velocities, int32_t behind,
+                                    int32_t ahead, double* smoothed, double* window_mean)
+{
+    using namespace acmpc::mapqp;
+    if (!h || !velocities || n < kSgWindow || behind < 0 || ahead < 0 || behind + ahead < 1) return ACMPC_ERR_INVALID;
+    if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    SavgolCoeffs c;
+    savgol_weights(0.0, c.interior);
+    for (int i = 0; i < kSgHalf; ++i) savgol_weights((double)(i - kSgHalf), c.edge[i]);
+    double* d = nullptr;
+    const size_t nb = (size_t)n * 8;
+    if (fail(h, cudaMalloc((void**)&d, 3 * nb), "cudaMalloc(reference speeds)")) return ACMPC_ERR_CUDA;
+    double *d_v = d, *d_s = d + n, *d_w = d + 2 * (size_t)n;
+    cudaStream_t st = h->stream;
+    const int threads = 128, blocks = (n + threads - 1) / threads;
+    int32_t rc = ACMPC_OK;
+    if (fail(h, cudaMemcpyAsync(d_v, velocities, nb, cudaMemcpyHostToDevice, st), "H2D(velocities)")) rc = ACMPC_ERR_CUDA;
+    if (rc == ACMPC_OK) {
+        acmpc_savgol_kernel<<<blocks, threads, 0, st>>>(d_v, n, c, d_s);
+        acmpc_window_mean_kernel<<<blocks, threads, 0, st>>>(d_s, n, behind, ahead, d_w);
+        if (fail(h, cudaGetLastError(), "reference speed kernels") ||
+            (smoothed && fail(h, cudaMemcpyAsync(smoothed, d_s, nb, cudaMemcpyDeviceToHost, st), "D2H(smoothed)")) ||
+            (window_mean && fail(h, cudaMemcpyAsync(window_mean, d_w, nb, cudaMemcpyDeviceToHost, st), "D2H(window mean)")) ||
+            fail(h, cudaStreamSynchronize(st), "reference speed kernels"))
+            rc = ACMPC_ERR_CUDA;
+    }
+    cudaFree(d);
+    if (rc == ACMPC_OK) h->last_launches = 2, h->last_smem = 0, h->last_threads = threads, h->last_ipc = 1;
+    return rc;
 }
 
 }  // extern "C"

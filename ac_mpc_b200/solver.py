@@ -141,6 +141,66 @@ class BatchedMPC:
                                                      int(bool(is_localised)), int(bool(keep_warm)), C.byref(o)))
         return out
 
+    # -- whole-track speed profile -----------------------------------
+    @staticmethod
+    def _map_info(info: "_capi.MapInfo") -> Dict:
+        return dict(status=int(info.status), status_str=_capi.STATUS_STRINGS.get(int(info.status), str(info.status)),
+                    iters=int(info.iters), rho_updates=int(info.rho_updates), ctas=int(info.ctas),
+                    pri_res=float(info.pri_res), dua_res=float(info.dua_res), obj_val=float(info.obj_val),
+                    rho=float(info.rho), kernel_ms=float(info.kernel_ms))
+
+    def construct_waypoints(self, track) -> np.ndarray:
+        """spatial_mpc.py:125-154 over an (M,3) array -> (7, M-1) rows (acmpc_construct_waypoints_host)."""
+        track = np.ascontiguousarray(track, dtype=np.float64)
+        if track.ndim != 2 or track.shape[1] != 3 or track.shape[0] < 3:
+            raise ValueError(f"track must be (M, 3) with M >= 3, got {track.shape}")
+        way = np.zeros((7, track.shape[0] - 1))
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_construct_waypoints_host(self._handle(), track.shape[0], track.ctypes.data_as(dp),
+                                                             way.ctypes.data_as(dp)))
+        return way
+
+    def map_speed_profile(self, waypoints: np.ndarray, v_max: float, ay_max: float, a_min: float,
+                          max_iter: int = 0):
+        """spatial_mpc.py:60-87 on a (7,n) ReferencePath array, IN PLACE (velocities row written when "solved").
+        Returns (dec_x, info dict)."""
+        if not (isinstance(waypoints, np.ndarray) and waypoints.dtype == np.float64 and waypoints.ndim == 2
+                and waypoints.shape[0] == 7 and waypoints.flags.c_contiguous):
+            raise ValueError("waypoints must be a C-contiguous float64 (7, n) array")
+        n = waypoints.shape[1]
+        x = np.zeros(n)
+        info = _capi.MapInfo()
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_map_speed_profile_host(self._handle(), n, waypoints.ctypes.data_as(dp), float(v_max),
+                                                           float(ay_max), float(a_min), int(max_iter),
+                                                           x.ctypes.data_as(dp), C.byref(info)))
+        return x, self._map_info(info)
+
+    def track_speed_profile(self, track, v_max: float, ay_max: float, a_min: float, max_iter: int = 0):
+        """controller.py:49-57 in one launch: (M,3) track -> ((7, M-1) rows incl. velocities, dec_x, info)."""
+        track = np.ascontiguousarray(track, dtype=np.float64)
+        if track.ndim != 2 or track.shape[1] != 3 or track.shape[0] < 3:
+            raise ValueError(f"track must be (M, 3) with M >= 3, got {track.shape}")
+        n = track.shape[0] - 1
+        way, x, info = np.zeros((7, n)), np.zeros(n), _capi.MapInfo()
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_track_speed_profile_host(self._handle(), track.shape[0], track.ctypes.data_as(dp),
+                                                             float(v_max), float(ay_max), float(a_min), int(max_iter),
+                                                             way.ctypes.data_as(dp), x.ctypes.data_as(dp),
+                                                             C.byref(info)))
+        return way, x, self._map_info(info)
+
+    def reference_speeds(self, velocities, behind: int = 25, ahead: int = 75):
+        """agent.py:300 + agent.py:137-143: (savgol_filter(v, 21, 3), window mean for every map index)."""
+        v = np.ascontiguousarray(velocities, dtype=np.float64)
+        if v.ndim != 1 or v.shape[0] < 21:
+            raise ValueError("velocities must be a vector of at least 21 samples")
+        sm, wm = np.zeros_like(v), np.zeros_like(v)
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_reference_speeds_host(self._handle(), v.shape[0], v.ctypes.data_as(dp), int(behind),
+                                                          int(ahead), sm.ctypes.data_as(dp), wm.ctypes.data_as(dp)))
+        return sm, wm
+
     # -- device buffers -------------------------------------------------------------------------
     def alloc_device_outputs(self, B: int, fields=None):
         """One packed uint8 CUDA tensor with a 256-byte aligned slab per field (so a multi-GPU run

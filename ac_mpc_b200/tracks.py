@@ -34,6 +34,20 @@ RACING_CONTROL = {
     "bathurst": dict(v_min=8.0, a_min=-1.0, ay_max=3.0, ki_min=0.0, end_velocity=14.0, step_cost=[1e-3, 2e-2, 0.0]),
 }
 
+# map_speed_profile_constraints blocks of /root/reference/configs/<track>.yaml (controller.py:89-91)
+MAP_PROFILE = {
+    "monza": dict(ay_max=7.0, a_min=-0.15), "spa": dict(ay_max=6.5, a_min=-0.15),
+    "silverstone": dict(ay_max=8.0, a_min=-0.1), "vallelunga": dict(ay_max=5.0, a_min=-0.15),
+    "yas_marina": dict(ay_max=2.0, a_min=-0.15), "bathurst": dict(ay_max=2.0, a_min=-0.15),
+    "nordschleife": dict(ay_max=2.0, a_min=-0.15),
+}
+ROAD_WIDTH_MAP = 9.5   # agent.py:288
+
+
+def map_track(centreline: np.ndarray) -> np.ndarray:
+    """(M,3) input of Controller.compute_track_speed_profile, as agent.py:287-296 builds it."""
+    return np.column_stack([centreline[:, 0], centreline[:, 1], np.full(len(centreline), ROAD_WIDTH_MAP)])
+
 
 def racing_config(track: str = "monza", horizon: int = 50) -> dict:
     """The dict `build_mpc` receives (controller.py:19-29) for a track's racing.control block."""

@@ -154,6 +154,46 @@ int32_t acmpc_collect_kernel_ms(acmpc_handle *h, double *speed_ms, double *contr
  * denominator for this path, MEASURED_PEAKS.json has no FP64 figure.  Returns TFLOP/s. */
 int32_t acmpc_fp64_peak_tflops(int32_t device, double *tflops);
 
+/* ---- Whole-track speed profile -------------------------------------------------
+ * The start-up path Controller.compute_track_speed_profile (controller.py:49-57): construct_waypoints over the
+ * whole centre line (spatial_mpc.py:125-154), then compute_map_speed_profile (spatial_mpc.py:60-87) = ONE
+ * speed-profile QP (solvers/speed_profile.py:26-86) with n = M - 1 ~ 10^4 variables and max_iter = 40000, then
+ * agent.py:287-302 / :137-143 (savgol_filter(v, 21, 3), [-25, +75) window mean with wrap-around).
+ * One cooperative launch: one stage per thread, 512 threads per CTA, so n <= 512 * (SMs of the device). */
+#define ACMPC_MAP_MAX_ITER 40000 /* MAX_SOLVER_ITERATIONS_MAP, spatial_mpc.py:16 */
+
+typedef struct acmpc_map_info {
+    int32_t status;      /* OSQP status of the QP (ACMPC_SOLVED ...) */
+    int32_t iters;       /* ADMM iterations */
+    int32_t rho_updates; /* refactorisations caused by adaptive rho */
+    int32_t ctas;        /* CTAs of the cooperative launch */
+    double pri_res, dua_res, obj_val, rho;
+    double kernel_ms;    /* device time of the launch (CUDA events) */
+} acmpc_map_info;
+
+/* SpatialMPC.construct_waypoints (spatial_mpc.py:125-154) over an (M,3) host array of (x, y, width):
+ * waypoints[7, M-1] = rows xs ys psis kappas distances widths velocities(= 0). */
+int32_t acmpc_construct_waypoints_host(acmpc_handle *h, int32_t M, const double *track, double *waypoints);
+
+/* SpatialMPC.compute_map_speed_profile (spatial_mpc.py:60-87) on a ReferencePath: reads the kappas and
+ * distances rows of waypoints[7,n] (host), writes the velocities row when the QP is "solved" and leaves it
+ * untouched otherwise (spatial_mpc.py:115-123).  v_max = the live speed_profile_constraints["v_max"]; the other
+ * constraints come from the handle's config with a_min / ay_max replaced (the deep copy of spatial_mpc.py:80-82).
+ * max_iter <= 0 selects ACMPC_MAP_MAX_ITER.  solution (may be NULL) receives dec.x whatever the status. */
+int32_t acmpc_map_speed_profile_host(acmpc_handle *h, int32_t n, double *waypoints, double v_max, double ay_max,
+                                     double a_min, int32_t max_iter, double *solution, acmpc_map_info *info);
+
+/* Both steps in one launch, straight from the (M,3) track (controller.py:49-57). */
+int32_t acmpc_track_speed_profile_host(acmpc_handle *h, int32_t M, const double *track, double v_max,
+                                       double ay_max, double a_min, int32_t max_iter, double *waypoints,
+                                       double *solution, acmpc_map_info *info);
+
+/* agent.py:300 reference_speeds = savgol_filter(velocities, 21, 3) -> smoothed[n], and agent.py:137-143 for EVERY
+ * map index c: window_mean[c] = mean(smoothed[(c - behind .. c + ahead) mod n]) (the reference uses 25 / 75).
+ * Either output may be NULL.  n >= 21. */
+int32_t acmpc_reference_speeds_host(acmpc_handle *h, int32_t n, const double *velocities, int32_t behind,
+                                    int32_t ahead, double *smoothed, double *window_mean);
+
 #ifdef __cplusplus
 }
 #endif

@@ -325,3 +325,55 @@ def solve_batch(cfg: Config, paths, offsets=None, vmax=None, is_localised=False,
     if rc != 0:
         raise RuntimeError("acmpc_port_solve_batch failed")
     return arrs
+
+
+# ---- whole-track speed profile -------------------------------------------------
+def construct_waypoints(coords) -> np.ndarray:
+    """numpy restatement of SpatialMPC.construct_waypoints (/root/reference/src/acmpc/control/
+    spatial_mpc.py:125-154) over an (M,3) array -> (7, M-1) ReferencePath rows (velocities = 0)."""
+    c = np.asarray(coords, dtype=np.float64)
+    cur, nxt = c[:-1, :2], c[1:, :2]
+    prev = np.vstack([c[-1:, :2], c[:-2, :2]])          # :135-137: "previous" of point 0 is the last point
+    a, b = nxt - cur, cur - prev
+    psi = np.arctan2(a[:, 1], a[:, 0])
+    d = np.sqrt(a[:, 0] ** 2 + a[:, 1] ** 2)
+    behind = np.arctan2(b[:, 1], b[:, 0])
+    dang = np.mod(psi - behind + np.pi, 2 * np.pi) - np.pi
+    kap = dang / (d + 1e-12) + 1e-12
+    kap[0] = kap[1]
+    out = np.zeros((7, len(d)))
+    out[0], out[1], out[2], out[3], out[4], out[5] = cur[:, 0], cur[:, 1], psi, kap, d, c[1:, 2]
+    return out
+
+
+def map_speed_profile(waypoints, constraints: dict, ay_max: float, a_min: float, max_iter: int = 40000,
+                      **settings):
+    """compute_map_speed_profile (spatial_mpc.py:60-87) = SpeedProfileSolver.solve (solvers/speed_profile.py:
+    15-86, end_velocity None) on a (7,n) ReferencePath array, through the C OSQP restatement.
+    Returns (x, info) -- `x` is dec.x; the caller assigns velocities only if info.status == 1."""
+    from scipy import sparse
+
+    w = np.asarray(waypoints, dtype=np.float64)
+    kap, d = w[3], w[4]
+    n = w.shape[1]
+    v_max = np.full(n, float(constraints["v_max"]))
+    v_dyn = np.sqrt(ay_max / (np.abs(kap) + 1e-12))
+    v_dyn[np.abs(kap) < constraints["ki_min"]] = constraints["v_max"]
+    vb = np.maximum(constraints["v_min"], np.minimum(v_dyn, v_max)) + 2.0
+    D1 = sparse.diags([-1 / (2 * d[:-1]), 1 / (2 * d[:-1])], offsets=[0, 1], shape=[n - 1, n])
+    A = sparse.vstack([D1, sparse.eye(n)], format="csc")
+    lo = np.hstack([np.full(n - 1, float(a_min)), np.full(n, float(constraints["v_min"]))])
+    hi = np.hstack([np.full(n - 1, float(constraints["a_max"])), vb])
+    solver = PortOSQP(sparse.eye(n, format="csc"), -1 * vb, A, lo, hi, max_iter=max_iter, **settings)
+    x, _, info = solver.solve()
+    return x, info
+
+
+def reference_speeds(velocities, behind: int = 25, ahead: int = 75):
+    """agent.py:300 (savgol_filter(v, 21, 3)) and agent.py:137-143 for every map index."""
+    from scipy.signal import savgol_filter
+
+    sm = savgol_filter(np.asarray(velocities, dtype=np.float64), 21, 3)
+    n = len(sm)
+    idx = (np.arange(n)[:, None] + np.arange(-behind, ahead)[None, :])
+    return sm, np.mean(sm.take(idx, mode="wrap"), axis=1)
