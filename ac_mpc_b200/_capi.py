@@ -12,7 +12,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libacmpc_b200.so")
+# ACMPC_B200_LIB: load another build of the same sources (instrumented experiments under tools/)
+LIB_PATH = os.environ.get("ACMPC_B200_LIB") or os.path.join(CSRC, "libacmpc_b200.so")
 _SOURCES = [os.path.join(CSRC, "acmpc_b200.cu"), os.path.join(CSRC, "mpc_warp.cuh"), os.path.join(CSRC, "simt.cuh"),
             os.path.join(CSRC, "map_profile.cuh"),
             os.path.join(os.path.dirname(_HERE), "include", "acmpc_b200.h")]

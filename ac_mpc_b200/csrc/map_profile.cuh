@@ -19,8 +19,8 @@
 //     solve is two affine scans y_s = r_s + N_s y_{s-1},  x_s = y_s/d_s + N_{s+1} x_{s+1}, run on three levels:
 //     Kogge-Stone over the 32 lanes with precomputed prefix products (5 FMAs + 5 shuffles), an affine scan over
 //     the CTA's 16 warp aggregates by warp 0, and a chain over the CTA aggregates through L2: every CTA publishes
-//     ONE (alpha, beta) pair, passes the grid barrier and folds the pairs of the CTAs before it.
-//     => two grid barriers per ADMM iteration and no other global traffic.
+//     ONE (alpha, beta) pair as flag-in-data words and folds the pairs of the CTAs before it as they arrive.
+//     => two L2 round trips per ADMM iteration, no barrier and no other global traffic in the iteration.
 //   * neighbour values ride on the scans: the term a_{s-1}(rho z - y)_{s-1} that stage s-1 contributes to r_s is
 //     folded into the forward chain ("g form": the carry entering a warp is g = t_prev + N_first y_prev), and the
 //     x~_{s+1} that row s needs IS the backward carry.
@@ -49,7 +49,8 @@ struct MapParams {
     double* solution;      // [n] dec.x (unscaled iterate at termination) or nullptr
     double* info;          // [8] status iter rho_updates pri_res dua_res obj_val rho -
     unsigned* counter;     // grid barrier arrivals (zero at launch)
-    double2* slots;        // [2][kMaxCtas + 1] CTA aggregates of the chain, by barrier parity
+    ulonglong4* slots;     // [2][ctas][ctas] inboxes of the chain: [chain parity][consumer position][producer position],
+                           // one CTA aggregate as four flag-in-data words each
     double* halo;          // [2][2][kMaxCtas * kWarps]
     double* red;           // [2][kMaxCtas][kRed]
     double* kd;            // [grid * kThreads] K diagonal -> 1/pivot
@@ -90,12 +91,13 @@ struct Grid {
     const MapParams& p;
     Shared& sh;
     int lane, warp, cta, ncta, s, n;
-    unsigned epoch;
+    unsigned epoch;    // grid barriers passed (arrival counter target)
+    unsigned chains;   // chain steps taken (tag of the aggregates; odd = forward, even = backward)
     int hbuf, rbuf;
 
     AC_MEM Grid(const MapParams& pp, Shared& ss)
         : p(pp), sh(ss), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), cta(blockIdx.x), ncta(gridDim.x),
-          s(blockIdx.x * kThreads + threadIdx.x), n(pp.n), epoch(0), hbuf(0), rbuf(0)
+          s(blockIdx.x * kThreads + threadIdx.x), n(pp.n), epoch(0), chains(0), hbuf(0), rbuf(0)
     {
     }
 
@@ -165,11 +167,34 @@ struct Grid {
     }
 
     // Warp 0 only, between two __syncthreads: affine scan over the CTA's 16 (alpha, beta) pairs (slot 0 = the
-    // identity = the carry entering the CTA), publish the CTA aggregate at chain position `pos`, grid barrier,
-    // fold the aggregates of positions < pos, and leave the carry entering each warp in carry[0..16).
+    // identity = the carry entering the CTA), publish the CTA aggregate at chain position `pos`, fold the aggregates
+    // of positions < pos as they arrive, and leave the carry entering each warp in carry[0..16).
+    // There is no barrier: an aggregate travels as four 8-byte words {32 data bits | 32-bit tag = chain step}
+    // (8-byte accesses are single-copy atomic, so a word whose tag matches carries valid data -- NCCL's LL
+    // protocol), and a CTA waits only for the CTAs before it in the chain.  Two buffers by chain parity are enough
+    // because forward and backward chains alternate: a CTA can publish step E+2 only after it has folded step
+    // E+1, i.e. after every consumer of its step-E aggregate has published E+1, which it does after reading E.
+#ifdef ACMPC_MAP_TIMING
+    long long c_pre = 0, c_poll = 0, c_post = 0, c_spins = 0;
+    unsigned long long gts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static __device__ __forceinline__ unsigned long long gtime()
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        return t;
+    }
+#define MAP_GT(k) \
+    if (chains == 2001u + ((k) >> 2) && l == 0) gts[k] = gtime();
+#else
+#define MAP_GT(k)
+#endif
     AC_MEM void chain(const double* a17, const double* b17, double* carry, int pos)
     {
+#ifdef ACMPC_MAP_TIMING
+        const long long tc0 = clock64();
+#endif
         const int l = lane;
+        MAP_GT((chains & 1u) ? 0 : 4);
         const bool in = l >= 1 && l <= kWarps;
         double A = in ? a17[l] : 1.0, B = in ? b17[l] : 0.0;
         AC_UNROLL
@@ -177,20 +202,72 @@ struct Grid {
             const double Ap = __shfl_up_sync(kFull, A, d), Bp = __shfl_up_sync(kFull, B, d);
             if (l >= d) B = fma(A, Bp, B), A = A * Ap;
         }
-        double2* slot = p.slots + (size_t)(epoch & 1u) * (kMaxCtas + 1);
-        if (l == kWarps) __stcg(slot + pos + 1, make_double2(A, B));
-        __syncwarp();
-        if (l == 0) arrive_and_wait(p.counter, epoch * (unsigned)ncta);
-        __syncwarp();
+        // push: the aggregate goes into a private inbox slot of EVERY consumer (the CTAs after this one in the
+        // chain), so each inbox line has exactly one polling CTA.  (With one shared slot per producer, polled by
+        // all its consumers, an update took 1-3 us to reach some of the pollers; a line with a single poller
+        // sees it in 0.25-0.45 us: tools/flag_latency_probe.cu, tools/chain_probe.cu.)
+        const unsigned long long tag = (unsigned long long)chains << 32;
+        ulonglong4* inbox = p.slots + (size_t)(chains & 1u) * ncta * ncta;   // [consumer position][producer position]
         const int per = (ncta + 31) >> 5;
-        double FA = 1.0, FB = 0.0;
-        for (int k = 0; k < per; ++k) {
-            const int idx = l * per + k + 1;
-            if (idx <= pos) {
-                const double2 v = ld_cg2(slot + idx);
-                FB = fma(v.x, FB, v.y), FA = v.x * FA;
+        {
+            const unsigned long long a = (unsigned long long)__double_as_longlong(__shfl_sync(kFull, A, kWarps)),
+                                     b = (unsigned long long)__double_as_longlong(__shfl_sync(kFull, B, kWarps));
+            for (int k = 0; k < per; ++k) {
+                const int cpos = pos + 1 + l + 32 * k;
+                if (cpos < ncta) {
+                    unsigned long long* w = (unsigned long long*)(inbox + (size_t)cpos * ncta + pos);
+                    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"((a & 0xffffffffull) | tag),
+                                 "l"((a >> 32) | tag)
+                                 : "memory");
+                    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(w + 2),
+                                 "l"((b & 0xffffffffull) | tag), "l"((b >> 32) | tag)
+                                 : "memory");
+                }
             }
         }
+        __syncwarp();
+        MAP_GT((chains & 1u) ? 1 : 5);
+#ifdef ACMPC_MAP_TIMING
+        const long long tc1 = clock64();
+        c_pre += tc1 - tc0;
+#endif
+        double FA = 1.0, FB = 0.0;
+        for (int k = 0; k < per; ++k) {
+            const int j = l * per + k;   // producer position
+            if (j < pos) {
+                const unsigned long long* w = (const unsigned long long*)(inbox + (size_t)pos * ncta + j);
+                unsigned long long w0, w1, w2, w3;
+                unsigned spins = 0;
+                for (;;) {
+                    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(w) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(w + 2) : "memory");
+                    if ((unsigned)(w0 >> 32) == chains && (unsigned)(w1 >> 32) == chains &&
+                        (unsigned)(w2 >> 32) == chains && (unsigned)(w3 >> 32) == chains)
+                        break;
+#ifdef ACMPC_MAP_TIMING
+                    ++c_spins;
+#endif
+#ifdef ACMPC_MAP_BACKOFF
+                    __nanosleep(ACMPC_MAP_BACKOFF);
+#endif
+                    if ((++spins & 1023u) == 0u) {   // see arrive_and_wait
+                        if (*(volatile unsigned*)(p.counter + 1) != 0u) break;
+                        if (spins > (1u << 22)) {
+                            *(volatile unsigned*)(p.counter + 1) = 1u;
+                            break;
+                        }
+                    }
+                }
+                const double va = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+                const double vb = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
+                FB = fma(va, FB, vb), FA = va * FA;
+            }
+        }
+        MAP_GT((chains & 1u) ? 2 : 6);
+#ifdef ACMPC_MAP_TIMING
+        const long long tc2 = clock64();
+        c_poll += tc2 - tc1;
+#endif
         AC_UNROLL
         for (int d = 1; d < 32; d <<= 1) {
             const double Ap = __shfl_up_sync(kFull, FA, d), Bp = __shfl_up_sync(kFull, FB, d);
@@ -198,10 +275,30 @@ struct Grid {
         }
         const double Gin = __shfl_sync(kFull, FB, 31);
         if (l < kWarps) carry[l] = fma(A, Gin, B);
+        MAP_GT((chains & 1u) ? 3 : 7);
+#ifdef ACMPC_MAP_TIMING
+        c_post += clock64() - tc2;
+#endif
     }
 };
 
+#ifdef ACMPC_MAP_TIMING
+#define MAP_TICK(k)                                  \
+    do {                                             \
+        const long long now_ = clock64();            \
+        tick[k] += now_ - tlast;                     \
+        tlast = now_;                                \
+    } while (0)
+#else
+#define MAP_TICK(k) \
+    do {            \
+    } while (0)
+#endif
+
 struct MapQP {
+#ifdef ACMPC_MAP_TIMING
+    long long tick[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#endif
     Grid& g;
     const acmpc_config& cfg;
     double al, au, ss, p, q, la, ua, lb, ub, di, eai, ebi;
@@ -354,24 +451,33 @@ struct MapQP {
     AC_MEM void kkt_solve(double r, double t, double& xt, double& xn)
     {
         const int lane = g.lane, warp = g.warp;
+        MAP_TICK(0);
         const double tp = __shfl_up_sync(kFull, t, 1);
         double Y = lane > 0 ? r + tp : r;
         AC_UNROLL
         for (int L = 0; L < kLevels; ++L) Y = fma(phi[L], __shfl_up_sync(kFull, Y, 1 << L), Y);
         if (lane == 31) g.sh.fb[warp + 1] = fma(M, Y, t);
+        MAP_TICK(1);
         __syncthreads();
-        ++g.epoch;
+        MAP_TICK(2);
+        ++g.chains;
         if (warp == 0) g.chain(g.sh.fa, g.sh.fb, g.sh.gcar, g.cta);
+        MAP_TICK(3);
         __syncthreads();
+        MAP_TICK(4);
         const double y = fma(Qw, g.sh.gcar[warp], Y);
         double Z = y * dinv;
         AC_UNROLL
         for (int L = 0; L < kLevels; ++L) Z = fma(psi[L], __shfl_down_sync(kFull, Z, 1 << L), Z);
         if (lane == 0) g.sh.bb[kWarps - warp] = Z;
+        MAP_TICK(5);
         __syncthreads();
-        ++g.epoch;
+        MAP_TICK(6);
+        ++g.chains;
         if (warp == 0) g.chain(g.sh.ba, g.sh.bb, g.sh.ccar, g.ncta - 1 - g.cta);
+        MAP_TICK(7);
         __syncthreads();
+        MAP_TICK(8);
         const double c = g.sh.ccar[kWarps - 1 - warp];
         xt = fma(Pb, c, Z);
         const double nx = __shfl_down_sync(kFull, xt, 1);
@@ -485,6 +591,9 @@ struct MapQP {
         x = za = zb = ya = yb = 0.0;
         dx = dya = dyb = 0.0;
         factor();
+#ifdef ACMPC_MAP_TIMING
+        tlast = clock64();
+#endif
         Norms N;
         int status = 0, iter = 0, updates = 0;
         int to_check = cfg.check_termination > 0 ? cfg.check_termination : -1;
@@ -497,6 +606,7 @@ struct MapQP {
             if (adapt) to_adapt = cfg.adaptive_rho_interval;
             const bool last = iter >= cfg.max_iter;
             iterate(alpha, sigma);
+            MAP_TICK(9);
             if (checked || adapt || last) {
                 compute_norms(N);
                 if (checked) status = check(N, 0);
@@ -514,8 +624,19 @@ struct MapQP {
                     if (status == 0) status = ACMPC_MAX_ITER_REACHED;
                 }
                 if (status != 0) break;
+                MAP_TICK(10);
             }
         }
+#ifdef ACMPC_MAP_TIMING
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < 12; ++k) g.p.red[2 * kMaxCtas * kRed + g.cta * 12 + k] = (double)tick[k];
+            // lane 0 polls the aggregate of chain position 0
+            g.p.red[2 * kMaxCtas * kRed + g.cta * 12 + 10] = (double)g.c_poll;
+            g.p.red[2 * kMaxCtas * kRed + g.cta * 12 + 11] = (double)g.c_spins;
+            for (int k = 0; k < 8; ++k)
+                g.p.red[2 * kMaxCtas * kRed + g.cta * 12 + k] = (double)(g.gts[k] % 100000000ull);
+        }
+#endif
         info.status = status, info.iter = iter, info.rho_updates = updates;
         info.pri_res = N.pri, info.dua_res = N.dua;
         double v[1] = {0.5 * p * x * x + q * x};
