@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # ACMPC_B200_LIB: load another build of the same sources (instrumented experiments under tools/)
 LIB_PATH = os.environ.get("ACMPC_B200_LIB") or os.path.join(CSRC, "libacmpc_b200.so")
 _SOURCES = [os.path.join(CSRC, "acmpc_b200.cu"), os.path.join(CSRC, "mpc_warp.cuh"), os.path.join(CSRC, "simt.cuh"),
-            os.path.join(CSRC, "map_profile.cuh"),
+            os.path.join(CSRC, "map_profile.cuh"), os.path.join(CSRC, "publish.cuh"),
             os.path.join(os.path.dirname(_HERE), "include", "acmpc_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -28,6 +28,8 @@ EXPORTED = [
     "acmpc_fp64_peak_tflops", "acmpc_set_profiling", "acmpc_collect_kernel_ms",
     "acmpc_construct_waypoints_host", "acmpc_map_speed_profile_host", "acmpc_track_speed_profile_host",
     "acmpc_reference_speeds_host",
+    "acmpc_reference_paths_host", "acmpc_publish_host", "acmpc_select_commands_f32_host",
+    "acmpc_select_commands_f64_host",
 ]
 
 RC_NAMES = {0: "ACMPC_OK", 1: "ACMPC_ERR_INVALID", 2: "ACMPC_ERR_CUDA", 3: "ACMPC_ERR_NO_DEVICE"}
@@ -156,6 +158,15 @@ def load() -> C.CDLL:
     L.acmpc_track_speed_profile_host.restype = C.c_int32
     L.acmpc_reference_speeds_host.argtypes = [vp, C.c_int32, dp, C.c_int32, C.c_int32, dp, dp]
     L.acmpc_reference_speeds_host.restype = C.c_int32
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    L.acmpc_reference_paths_host.argtypes = [vp, C.c_int32, C.c_int32, fp, dp]
+    L.acmpc_reference_paths_host.restype = C.c_int32
+    L.acmpc_publish_host.argtypes = [vp, C.c_int32, dp, dp, dp, fp, fp, fp]
+    L.acmpc_publish_host.restype = C.c_int32
+    L.acmpc_select_commands_f32_host.argtypes = [vp, C.c_int32, C.c_int32, fp, fp, dp, C.c_int32, fp, ip]
+    L.acmpc_select_commands_f32_host.restype = C.c_int32
+    L.acmpc_select_commands_f64_host.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, C.c_int32, dp, ip]
+    L.acmpc_select_commands_f64_host.restype = C.c_int32
     _lib = L
     return L
 

@@ -23,6 +23,7 @@
 
 #include "mpc_warp.cuh"
 #include "map_profile.cuh"
+#include "publish.cuh"
 
 namespace {
 
@@ -1104,6 +1105,132 @@ int32_t acmpc_reference_speeds_host(acmpc_handle* h, int32_t n, const double* ve
     cudaFree(d);
     if (rc == ACMPC_OK) h->last_launches = 2, h->last_smem = 0, h->last_threads = threads, h->last_ipc = 1;
     return rc;
+}
+
+}  // extern "C"
+
+// ---- caller side of the step (publish.cuh) --------------------------------------------------------------------
+namespace {
+
+// small staged call: copy the inputs in, run `launch`, copy the outputs back, synchronise
+struct Staged {
+    acmpc_handle* h;
+    char* base = nullptr;
+    size_t used = 0, cap = 0;
+    int32_t rc = ACMPC_OK;
+    Staged(acmpc_handle* hh, size_t bytes) : h(hh), cap(bytes + 4096)
+    {
+        if (fail(h, cudaSetDevice(h->device), "cudaSetDevice") || fail(h, cudaMalloc((void**)&base, cap), "cudaMalloc(staged)"))
+            rc = ACMPC_ERR_CUDA;
+    }
+    ~Staged()
+    {
+        if (base) cudaFree(base);
+    }
+    void* in(const void* src, size_t bytes)
+    {
+        if (rc != ACMPC_OK || !src) return nullptr;
+        void* d = base + used;
+        used += (bytes + 255) & ~(size_t)255;
+        if (fail(h, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->stream), "H2D(staged)")) rc = ACMPC_ERR_CUDA;
+        return d;
+    }
+    void* out(const void* dst, size_t bytes)
+    {
+        if (rc != ACMPC_OK || !dst) return nullptr;
+        void* d = base + used;
+        used += (bytes + 255) & ~(size_t)255;
+        return d;
+    }
+    void back(void* dst, const void* d, size_t bytes)
+    {
+        if (rc != ACMPC_OK || !dst) return;
+        if (fail(h, cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, h->stream), "D2H(staged)")) rc = ACMPC_ERR_CUDA;
+    }
+    int32_t finish(int launches, int threads)
+    {
+        if (rc == ACMPC_OK && (fail(h, cudaGetLastError(), "publish kernels") || fail(h, cudaStreamSynchronize(h->stream), "publish kernels")))
+            rc = ACMPC_ERR_CUDA;
+        if (rc == ACMPC_OK) h->last_launches = launches, h->last_smem = 0, h->last_threads = threads, h->last_ipc = 1;
+        return rc;
+    }
+};
+
+template <typename T>
+int32_t select_commands(acmpc_handle* h, int32_t B, int32_t n, const T* cum_time, const T* commands, const double* elapsed,
+                        int32_t mode, T* out, int32_t* indices)
+{
+    if (!h || B < 1 || n < 1 || !cum_time || !commands || !elapsed || !out || (mode != 0 && mode != 1)) return ACMPC_ERR_INVALID;
+    const size_t nb = (size_t)B * n * sizeof(T);
+    Staged s(h, 3 * nb + (size_t)B * (8 + 2 * sizeof(T) + 8) + 8 * 256);
+    const T* d_ct = (const T*)s.in(cum_time, nb);
+    const T* d_cm = (const T*)s.in(commands, 2 * nb);
+    const double* d_el = (const double*)s.in(elapsed, (size_t)B * 8);
+    T* d_out = (T*)s.out(out, (size_t)B * 2 * sizeof(T));
+    int32_t* d_idx = (int32_t*)s.out(indices, (size_t)B * 8);
+    if (s.rc == ACMPC_OK)
+        acmpc::pub::select_commands_kernel<T><<<(B + 127) / 128, 128, 0, h->stream>>>(d_ct, d_cm, d_el, B, n, mode, d_out, d_idx);
+    s.back(out, d_out, (size_t)B * 2 * sizeof(T));
+    s.back(indices, d_idx, (size_t)B * 8);
+    return s.finish(1, 128);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t acmpc_reference_paths_host(acmpc_handle* h, int32_t B, int32_t P, const float* centrelines, double* paths)
+{
+    if (!h || B < 1 || !centrelines || !paths) return ACMPC_ERR_INVALID;
+    const int H = h->cfg.horizon;
+    if (P < H) return ACMPC_ERR_INVALID;
+    const int ds = P / H;                          // int(len(centreline) / horizon), controller.py:260
+    if ((P + ds - 1) / ds != H) {                  // centreline[0::ds] has another length: np.stack raises
+        h->err = "reference path: len(centreline[0::ds]) != horizon (the reference's np.stack raises here)";
+        return ACMPC_ERR_INVALID;
+    }
+    const size_t in_b = (size_t)B * P * 2 * sizeof(float), out_b = (size_t)B * H * 3 * 8;
+    Staged s(h, in_b + out_b);
+    const float* d_c = (const float*)s.in(centrelines, in_b);
+    double* d_p = (double*)s.out(paths, out_b);
+    if (s.rc == ACMPC_OK)
+        acmpc::pub::reference_paths_kernel<<<(B * H + 127) / 128, 128, 0, h->stream>>>(d_c, B, P, H, ds, d_p);
+    s.back(paths, d_p, out_b);
+    return s.finish(1, 128);
+}
+
+int32_t acmpc_publish_host(acmpc_handle* h, int32_t B, const double* controls, const double* cum_time,
+                           const double* prediction, float* control_inputs, float* control_cumtime,
+                           float* predicted_locations)
+{
+    if (!h || B < 1) return ACMPC_ERR_INVALID;
+    const int n = h->cfg.horizon - 1;
+    const size_t e = (size_t)B * n;
+    Staged s(h, e * (2 + 1 + 2) * (8 + 4) + 8 * 256);
+    const double* d_c = (const double*)s.in(control_inputs ? controls : nullptr, e * 2 * 8);
+    const double* d_t = (const double*)s.in(control_cumtime ? cum_time : nullptr, e * 8);
+    const double* d_p = (const double*)s.in(predicted_locations ? prediction : nullptr, e * 2 * 8);
+    float* o_c = (float*)s.out(d_c ? control_inputs : nullptr, e * 2 * 4);
+    float* o_t = (float*)s.out(d_t ? control_cumtime : nullptr, e * 4);
+    float* o_p = (float*)s.out(d_p ? predicted_locations : nullptr, e * 2 * 4);
+    if (s.rc == ACMPC_OK)
+        acmpc::pub::publish_kernel<<<((int)e + 127) / 128, 128, 0, h->stream>>>(d_c, d_t, d_p, B, n, o_c, o_t, o_p);
+    if (o_c) s.back(control_inputs, o_c, e * 2 * 4);
+    if (o_t) s.back(control_cumtime, o_t, e * 4);
+    if (o_p) s.back(predicted_locations, o_p, e * 2 * 4);
+    return s.finish(1, 128);
+}
+
+int32_t acmpc_select_commands_f32_host(acmpc_handle* h, int32_t B, int32_t n, const float* cum_time, const float* commands,
+                                       const double* elapsed, int32_t mode, float* out, int32_t* indices)
+{
+    return select_commands<float>(h, B, n, cum_time, commands, elapsed, mode, out, indices);
+}
+
+int32_t acmpc_select_commands_f64_host(acmpc_handle* h, int32_t B, int32_t n, const double* cum_time, const double* commands,
+                                       const double* elapsed, int32_t mode, double* out, int32_t* indices)
+{
+    return select_commands<double>(h, B, n, cum_time, commands, elapsed, mode, out, indices);
 }
 
 }  // extern "C"

@@ -201,6 +201,57 @@ class BatchedMPC:
                                                           int(ahead), sm.ctypes.data_as(dp), wm.ctypes.data_as(dp)))
         return sm, wm
 
+    # -- caller side of the step -------------------------------------
+    def reference_paths(self, centrelines) -> np.ndarray:
+        """ControlProcess._reference_path (controller.py:257-267) for B perceived centre lines:
+        (B,P,2) float32 -> (B,H,3) float64.  Raises where the reference's np.stack raises (P // H stride not
+        yielding H rows)."""
+        c = np.ascontiguousarray(centrelines, dtype=np.float32)
+        if c.ndim != 3 or c.shape[2] != 2:
+            raise ValueError(f"centrelines must be (B, P, 2), got {c.shape}")
+        out = np.empty((c.shape[0], self.H, 3))
+        self._check(self._lib.acmpc_reference_paths_host(self._handle(), c.shape[0], c.shape[1],
+                                                         c.ctypes.data_as(C.POINTER(C.c_float)),
+                                                         out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def publish(self, controls, cum_time, prediction):
+        """ControlProcess._update_shared_memory (controller.py:274-280): the float32 arrays the agent process reads,
+        (control_inputs (B,n,2) = projected_control.T, control_cumtime (B,n), predicted_locations (B,n,2))."""
+        controls = np.ascontiguousarray(controls, dtype=np.float64)
+        cum_time = np.ascontiguousarray(cum_time, dtype=np.float64)
+        prediction = np.ascontiguousarray(prediction, dtype=np.float64)
+        B, n = cum_time.shape
+        if n != self.n or controls.shape != (B, 2, n) or prediction.shape != (B, n, 2):
+            raise ValueError("controls (B,2,n), cum_time (B,n), prediction (B,n,2) expected")
+        ci, ct, pl = (np.empty((B, n, 2), np.float32), np.empty((B, n), np.float32), np.empty((B, n, 2), np.float32))
+        dp, fp = C.POINTER(C.c_double), C.POINTER(C.c_float)
+        self._check(self._lib.acmpc_publish_host(self._handle(), B, controls.ctypes.data_as(dp), cum_time.ctypes.data_as(dp),
+                                                 prediction.ctypes.data_as(dp), ci.ctypes.data_as(fp),
+                                                 ct.ctypes.data_as(fp), pl.ctypes.data_as(fp)))
+        return ci, ct, pl
+
+    def select_commands(self, cum_time, commands, elapsed, interpolate: bool = False, return_indices: bool = False):
+        """commands.py: TemporalCommandSelector (default) / TemporalCommandInterpolator lookup for B instances.
+        cum_time (B,n), commands (B,n,2), elapsed (B,).  float32 inputs are processed in float32 (the shared-memory
+        views), anything else in float64."""
+        cum_time = np.asarray(cum_time)
+        f32 = cum_time.dtype == np.float32
+        dt, ct_t = (np.float32, C.c_float) if f32 else (np.float64, C.c_double)
+        cum_time = np.ascontiguousarray(cum_time, dtype=dt)
+        commands = np.ascontiguousarray(commands, dtype=dt)
+        elapsed = np.ascontiguousarray(elapsed, dtype=np.float64)
+        B, n = cum_time.shape
+        if commands.shape != (B, n, 2) or elapsed.shape != (B,):
+            raise ValueError("cum_time (B,n), commands (B,n,2), elapsed (B,) expected")
+        out, idx = np.empty((B, 2), dt), np.empty((B, 2), np.int32)
+        fn = self._lib.acmpc_select_commands_f32_host if f32 else self._lib.acmpc_select_commands_f64_host
+        tp = C.POINTER(ct_t)
+        self._check(fn(self._handle(), B, n, cum_time.ctypes.data_as(tp), commands.ctypes.data_as(tp),
+                       elapsed.ctypes.data_as(C.POINTER(C.c_double)), int(bool(interpolate)), out.ctypes.data_as(tp),
+                       idx.ctypes.data_as(C.POINTER(C.c_int32))))
+        return (out, idx) if return_indices else out
+
     # -- device buffers -------------------------------------------------------------------------
     def alloc_device_outputs(self, B: int, fields=None):
         """One packed uint8 CUDA tensor with a 256-byte aligned slab per field (so a multi-GPU run

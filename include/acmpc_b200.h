@@ -194,6 +194,33 @@ int32_t acmpc_track_speed_profile_host(acmpc_handle *h, int32_t M, const double 
 int32_t acmpc_reference_speeds_host(acmpc_handle *h, int32_t n, const double *velocities, int32_t behind,
                                     int32_t ahead, double *smoothed, double *window_mean);
 
+/* ---- Caller side of the step, batched over B instances ------------------------------
+ * ControlProcess._reference_path (controller.py:257-267): perceived centre lines [B,P,2] float32 -> paths [B,H,3]
+ * float64 = rows 0::int(P/H) of (x, y) + widths linspace(10, 6, H).  Like the reference (np.stack raises) this is
+ * only defined when the stride yields exactly H rows; otherwise ACMPC_ERR_INVALID. */
+int32_t acmpc_reference_paths_host(acmpc_handle *h, int32_t B, int32_t P, const float *centrelines, double *paths);
+
+/* ControlProcess._update_shared_memory (controller.py:274-280) into the float32 shared arrays
+ * (perception/shared_memory.py:90-104): control_inputs[B,n,2] = projected_control.T, control_cumtime[B,n],
+ * predicted_locations[B,n,2].  Any input/output pair may be NULL. */
+int32_t acmpc_publish_host(acmpc_handle *h, int32_t B, const double *controls, const double *cum_time,
+                           const double *prediction, float *control_inputs, float *control_cumtime,
+                           float *predicted_locations);
+
+/* Command lookup at `elapsed[b]` seconds after the publish (controller.py:110-116):
+ * mode 0 = TemporalCommandSelector.get_command (commands.py:8-38, the production selector),
+ * mode 1 = TemporalCommandInterpolator.get_command (commands.py:41-99).
+ * cum_time[B,n], commands[B,n,2] (rows = (v, delta)), out[B,2]; indices (may be NULL) [B,2] = the command rows used.
+ * _f32 works on the float32 shared-memory views in float32, _f64 on float64 arrays (the reference's test vectors). */
+#define ACMPC_COMMAND_SELECT 0
+#define ACMPC_COMMAND_INTERPOLATE 1
+int32_t acmpc_select_commands_f32_host(acmpc_handle *h, int32_t B, int32_t n, const float *cum_time,
+                                       const float *commands, const double *elapsed, int32_t mode, float *out,
+                                       int32_t *indices);
+int32_t acmpc_select_commands_f64_host(acmpc_handle *h, int32_t B, int32_t n, const double *cum_time,
+                                       const double *commands, const double *elapsed, int32_t mode, double *out,
+                                       int32_t *indices);
+
 #ifdef __cplusplus
 }
 #endif

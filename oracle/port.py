@@ -377,3 +377,38 @@ def reference_speeds(velocities, behind: int = 25, ahead: int = 75):
     n = len(sm)
     idx = (np.arange(n)[:, None] + np.arange(-behind, ahead)[None, :])
     return sm, np.mean(sm.take(idx, mode="wrap"), axis=1)
+
+
+# ---- caller side of the step ----------------------------------------------------
+def select_command(cum_time, commands, elapsed_time: float):
+    """TemporalCommandSelector.get_command (/root/reference/src/acmpc/control/commands.py:22-35);
+    cum_time (n,), commands (n,2); arithmetic in the dtype of cum_time, as numpy does with a Python float."""
+    distances = cum_time - elapsed_time
+    index = int(np.argmin(abs(distances)))
+    if distances[index] > 0:
+        index -= 1
+    n = len(commands)
+    index = index if index < n else n - 1
+    return commands[index]            # index -1 = the last command, as in the reference
+
+
+def interpolate_command(cum_time, commands, elapsed_time: float):
+    """TemporalCommandInterpolator.get_command (commands.py:59-99); commands (n,2)."""
+    distances = cum_time - elapsed_time
+    a = int(np.argmin(abs(distances)))
+    if a == 0 or a == len(commands) - 1:
+        b = a
+    elif distances[a] < 0:
+        b = a + 1
+    else:
+        b = a - 1
+    if a == b:
+        return commands[a]
+    x_a, y_a, x_b, y_b = cum_time[a], commands[a], cum_time[b], commands[b]
+    return y_a * ((x_b - elapsed_time) / (x_b - x_a)) + y_b * ((elapsed_time - x_a) / (x_b - x_a))
+
+
+def reference_path(centreline, horizon: int):
+    """ControlProcess._reference_path (control/controller.py:257-267)."""
+    ds = int(len(centreline) / horizon)
+    return np.stack([centreline[0::ds, 0], centreline[0::ds, 1], np.linspace(10.0, 6.0, horizon)]).T
