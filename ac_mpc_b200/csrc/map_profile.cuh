@@ -231,33 +231,36 @@ struct Grid {
         const long long tc1 = clock64();
         c_pre += tc1 - tc0;
 #endif
+        // The poll loop is WARP-UNIFORM: every lane stays in it until all lanes have their aggregate (vote).  With a
+        // per-lane exit the warp leaves the loop diverged, and every later __shfl_*_sync of the warp takes the
+        // compiler's BRA.DIV slow path (a WARPSYNC.COLLECTIVE per SHFL): tools/chain_probe2.cu measured 5 k cycles
+        // for the 22 shuffles of the fold below instead of 600 -- two thirds of the whole ADMM iteration.
         double FA = 1.0, FB = 0.0;
         for (int k = 0; k < per; ++k) {
             const int j = l * per + k;   // producer position
-            if (j < pos) {
-                const unsigned long long* w = (const unsigned long long*)(inbox + (size_t)pos * ncta + j);
-                unsigned long long w0, w1, w2, w3;
-                unsigned spins = 0;
-                for (;;) {
+            bool ready = j >= pos;
+            const unsigned long long* w = (const unsigned long long*)(inbox + (size_t)pos * ncta + (ready ? 0 : j));
+            unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            unsigned spins = 0;
+            do {
+                if (!ready) {
                     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(w) : "memory");
                     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(w + 2) : "memory");
-                    if ((unsigned)(w0 >> 32) == chains && (unsigned)(w1 >> 32) == chains &&
-                        (unsigned)(w2 >> 32) == chains && (unsigned)(w3 >> 32) == chains)
-                        break;
+                    ready = (unsigned)(w0 >> 32) == chains && (unsigned)(w1 >> 32) == chains &&
+                            (unsigned)(w2 >> 32) == chains && (unsigned)(w3 >> 32) == chains;
+                }
 #ifdef ACMPC_MAP_TIMING
-                    ++c_spins;
+                ++c_spins;
 #endif
-#ifdef ACMPC_MAP_BACKOFF
-                    __nanosleep(ACMPC_MAP_BACKOFF);
-#endif
-                    if ((++spins & 1023u) == 0u) {   // see arrive_and_wait
-                        if (*(volatile unsigned*)(p.counter + 1) != 0u) break;
-                        if (spins > (1u << 22)) {
-                            *(volatile unsigned*)(p.counter + 1) = 1u;
-                            break;
-                        }
+                if ((++spins & 1023u) == 0u) {   // see arrive_and_wait
+                    if (*(volatile unsigned*)(p.counter + 1) != 0u) ready = true;
+                    if (spins > (1u << 22)) {
+                        *(volatile unsigned*)(p.counter + 1) = 1u;
+                        ready = true;
                     }
                 }
+            } while (!__all_sync(kFull, ready));
+            if (j < pos) {
                 const double va = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
                 const double vb = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
                 FB = fma(va, FB, vb), FA = va * FA;

@@ -26,6 +26,28 @@ __device__ __forceinline__ double chain(ulonglong4* slots, unsigned chains, int 
     __syncwarp();
     const int per = (ncta + 31) >> 5;
     double FA = 1.0, FB = 0.0;
+    if (VARIANT == 4) {
+        // warp-uniform polling: every lane stays in the loop until ALL lanes have their aggregate
+        for (int k = 0; k < per; ++k) {
+            const int idx = l * per + k + 1;
+            bool ready = idx > pos;
+            unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            const unsigned long long* w = (const unsigned long long*)(slot + (ready ? 0 : idx) * 4);
+            do {
+                if (!ready) {
+                    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(w) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(w + 2) : "memory");
+                    ready = (unsigned)(w0 >> 32) == chains && (unsigned)(w1 >> 32) == chains &&
+                            (unsigned)(w2 >> 32) == chains && (unsigned)(w3 >> 32) == chains;
+                }
+            } while (!__all_sync(kFull, ready));
+            if (idx <= pos) {
+                const double va = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+                const double vb = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
+                FB = fma(va, FB, vb), FA = va * FA;
+            }
+        }
+    } else
     for (int k = 0; k < per; ++k) {
         const int idx = l * per + k + 1;
         if (idx <= pos) {
@@ -44,6 +66,7 @@ __device__ __forceinline__ double chain(ulonglong4* slots, unsigned chains, int 
             FB = fma(va, FB, vb), FA = va * FA;
         }
     }
+    if (VARIANT == 3) __syncwarp();
     if (VARIANT != 2) {
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -106,6 +129,7 @@ int main()
             run<0>("as in map_profile.cuh", slots, d_cycles, sink, ncta, work);
             run<1>("one 16-byte word pair", slots, d_cycles, sink, ncta, work);
             run<2>("no second scan", slots, d_cycles, sink, ncta, work);
+            run<4>("warp-uniform poll loop (vote)", slots, d_cycles, sink, ncta, work);
         }
     return 0;
 }
