@@ -947,7 +947,7 @@ int32_t run_map(acmpc_handle* h, int M, int n, const double* h_track, double* h_
     p.M = M, p.n = n, p.do_solve = do_solve;
     const size_t way_b = (size_t)7 * n * 8, trk_b = h_track ? (size_t)3 * M * 8 : 0, k_b = (size_t)ctas * kThreads * 8;
     const size_t slots_b = (size_t)2 * ctas * ctas * sizeof(ulonglong4), halo_b = (size_t)2 * 2 * kMaxCtas * kWarps * 8,
-                 red_b = (size_t)2 * kMaxCtas * kRed * 8 + (size_t)kMaxCtas * 12 * 8;   // + ACMPC_MAP_TIMING ticks
+                 red_b = (size_t)2 * kMaxCtas * kRed * 8;
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t total = up(way_b) + up(trk_b) + up((size_t)n * 8) + 2 * up(k_b) + up(slots_b) + up(halo_b) +
                          up(red_b) + up(64) + 256;
@@ -986,17 +986,6 @@ int32_t run_map(acmpc_handle* h, int M, int n, const double* h_track, double* h_
         fail(h, cudaStreamSynchronize(st), "map profile kernel") ||
         fail(h, cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime"))
         rc = ACMPC_ERR_CUDA;
-#ifdef ACMPC_MAP_TIMING
-    if (rc == ACMPC_OK && do_solve) {
-        static double ticks[kMaxCtas * 12];
-        cudaMemcpy(ticks, p.red + 2 * kMaxCtas * kRed, sizeof(ticks), cudaMemcpyDeviceToHost);
-        for (int c = 0; c < ctas; ++c) {
-            fprintf(stderr, "map gt cta %3d:", c);
-            for (int k = 0; k < 8; ++k) fprintf(stderr, " %.0f", ticks[c * 12 + k] - ticks[0]);
-            fprintf(stderr, "  (ns: fwd entry/published/lane0 polled/done, bwd ...)\n");
-        }
-    }
-#endif
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     cudaFree(base);

@@ -174,27 +174,9 @@ struct Grid {
     // protocol), and a CTA waits only for the CTAs before it in the chain.  Two buffers by chain parity are enough
     // because forward and backward chains alternate: a CTA can publish step E+2 only after it has folded step
     // E+1, i.e. after every consumer of its step-E aggregate has published E+1, which it does after reading E.
-#ifdef ACMPC_MAP_TIMING
-    long long c_pre = 0, c_poll = 0, c_post = 0, c_spins = 0;
-    unsigned long long gts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    static __device__ __forceinline__ unsigned long long gtime()
-    {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        return t;
-    }
-#define MAP_GT(k) \
-    if (chains == 2001u + ((k) >> 2) && l == 0) gts[k] = gtime();
-#else
-#define MAP_GT(k)
-#endif
     AC_MEM void chain(const double* a17, const double* b17, double* carry, int pos)
     {
-#ifdef ACMPC_MAP_TIMING
-        const long long tc0 = clock64();
-#endif
         const int l = lane;
-        MAP_GT((chains & 1u) ? 0 : 4);
         const bool in = l >= 1 && l <= kWarps;
         double A = in ? a17[l] : 1.0, B = in ? b17[l] : 0.0;
         AC_UNROLL
@@ -226,11 +208,6 @@ struct Grid {
             }
         }
         __syncwarp();
-        MAP_GT((chains & 1u) ? 1 : 5);
-#ifdef ACMPC_MAP_TIMING
-        const long long tc1 = clock64();
-        c_pre += tc1 - tc0;
-#endif
         // The poll loop is WARP-UNIFORM: every lane stays in it until all lanes have their aggregate (vote).  With a
         // per-lane exit the warp leaves the loop diverged, and every later __shfl_*_sync of the warp takes the
         // compiler's BRA.DIV slow path (a WARPSYNC.COLLECTIVE per SHFL): tools/chain_probe2.cu measured 5 k cycles
@@ -249,9 +226,6 @@ struct Grid {
                     ready = (unsigned)(w0 >> 32) == chains && (unsigned)(w1 >> 32) == chains &&
                             (unsigned)(w2 >> 32) == chains && (unsigned)(w3 >> 32) == chains;
                 }
-#ifdef ACMPC_MAP_TIMING
-                ++c_spins;
-#endif
                 if ((++spins & 1023u) == 0u) {   // see arrive_and_wait
                     if (*(volatile unsigned*)(p.counter + 1) != 0u) ready = true;
                     if (spins > (1u << 22)) {
@@ -266,11 +240,6 @@ struct Grid {
                 FB = fma(va, FB, vb), FA = va * FA;
             }
         }
-        MAP_GT((chains & 1u) ? 2 : 6);
-#ifdef ACMPC_MAP_TIMING
-        const long long tc2 = clock64();
-        c_poll += tc2 - tc1;
-#endif
         AC_UNROLL
         for (int d = 1; d < 32; d <<= 1) {
             const double Ap = __shfl_up_sync(kFull, FA, d), Bp = __shfl_up_sync(kFull, FB, d);
@@ -278,30 +247,10 @@ struct Grid {
         }
         const double Gin = __shfl_sync(kFull, FB, 31);
         if (l < kWarps) carry[l] = fma(A, Gin, B);
-        MAP_GT((chains & 1u) ? 3 : 7);
-#ifdef ACMPC_MAP_TIMING
-        c_post += clock64() - tc2;
-#endif
     }
 };
 
-#ifdef ACMPC_MAP_TIMING
-#define MAP_TICK(k)                                  \
-    do {                                             \
-        const long long now_ = clock64();            \
-        tick[k] += now_ - tlast;                     \
-        tlast = now_;                                \
-    } while (0)
-#else
-#define MAP_TICK(k) \
-    do {            \
-    } while (0)
-#endif
-
 struct MapQP {
-#ifdef ACMPC_MAP_TIMING
-    long long tick[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-#endif
     Grid& g;
     const acmpc_config& cfg;
     double al, au, ss, p, q, la, ua, lb, ub, di, eai, ebi;
@@ -454,33 +403,24 @@ struct MapQP {
     AC_MEM void kkt_solve(double r, double t, double& xt, double& xn)
     {
         const int lane = g.lane, warp = g.warp;
-        MAP_TICK(0);
         const double tp = __shfl_up_sync(kFull, t, 1);
         double Y = lane > 0 ? r + tp : r;
         AC_UNROLL
         for (int L = 0; L < kLevels; ++L) Y = fma(phi[L], __shfl_up_sync(kFull, Y, 1 << L), Y);
         if (lane == 31) g.sh.fb[warp + 1] = fma(M, Y, t);
-        MAP_TICK(1);
         __syncthreads();
-        MAP_TICK(2);
         ++g.chains;
         if (warp == 0) g.chain(g.sh.fa, g.sh.fb, g.sh.gcar, g.cta);
-        MAP_TICK(3);
         __syncthreads();
-        MAP_TICK(4);
         const double y = fma(Qw, g.sh.gcar[warp], Y);
         double Z = y * dinv;
         AC_UNROLL
         for (int L = 0; L < kLevels; ++L) Z = fma(psi[L], __shfl_down_sync(kFull, Z, 1 << L), Z);
         if (lane == 0) g.sh.bb[kWarps - warp] = Z;
-        MAP_TICK(5);
         __syncthreads();
-        MAP_TICK(6);
         ++g.chains;
         if (warp == 0) g.chain(g.sh.ba, g.sh.bb, g.sh.ccar, g.ncta - 1 - g.cta);
-        MAP_TICK(7);
         __syncthreads();
-        MAP_TICK(8);
         const double c = g.sh.ccar[kWarps - 1 - warp];
         xt = fma(Pb, c, Z);
         const double nx = __shfl_down_sync(kFull, xt, 1);
@@ -594,9 +534,6 @@ struct MapQP {
         x = za = zb = ya = yb = 0.0;
         dx = dya = dyb = 0.0;
         factor();
-#ifdef ACMPC_MAP_TIMING
-        tlast = clock64();
-#endif
         Norms N;
         int status = 0, iter = 0, updates = 0;
         int to_check = cfg.check_termination > 0 ? cfg.check_termination : -1;
@@ -609,7 +546,6 @@ struct MapQP {
             if (adapt) to_adapt = cfg.adaptive_rho_interval;
             const bool last = iter >= cfg.max_iter;
             iterate(alpha, sigma);
-            MAP_TICK(9);
             if (checked || adapt || last) {
                 compute_norms(N);
                 if (checked) status = check(N, 0);
@@ -627,19 +563,8 @@ struct MapQP {
                     if (status == 0) status = ACMPC_MAX_ITER_REACHED;
                 }
                 if (status != 0) break;
-                MAP_TICK(10);
             }
         }
-#ifdef ACMPC_MAP_TIMING
-        if (threadIdx.x == 0) {
-            for (int k = 0; k < 12; ++k) g.p.red[2 * kMaxCtas * kRed + g.cta * 12 + k] = (double)tick[k];
-            // lane 0 polls the aggregate of chain position 0
-            g.p.red[2 * kMaxCtas * kRed + g.cta * 12 + 10] = (double)g.c_poll;
-            g.p.red[2 * kMaxCtas * kRed + g.cta * 12 + 11] = (double)g.c_spins;
-            for (int k = 0; k < 8; ++k)
-                g.p.red[2 * kMaxCtas * kRed + g.cta * 12 + k] = (double)(g.gts[k] % 100000000ull);
-        }
-#endif
         info.status = status, info.iter = iter, info.rho_updates = updates;
         info.pri_res = N.pri, info.dua_res = N.dua;
         double v[1] = {0.5 * p * x * x + q * x};

@@ -340,6 +340,29 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     pw = port.PortMPC(port.default_config(**kw))
     cpu_lat_warm_ms = p50(lambda i: pw.step(seq[i], 0.0, None, False, warm=True), 40)
 
+    launch_info = mpc.launch_info()
+    # start-up path (scope row 8f-1): the whole-track speed profile of the same track, one cooperative launch,
+    # next to the oracle's C OSQP port on one host core (solve only, its setup excluded).  Outside the timed steps.
+    map_line = None
+    if not args.no_map_profile:
+        trk = tracks.map_track(cl)
+        mp_c = tracks.MAP_PROFILE[args.track]
+        spc = tracks.racing_config(args.track)["speed_profile_constraints"]
+        best = None
+        for _ in range(3):
+            _, xg, mi = api._batched().track_speed_profile(trk, spc["v_max"], mp_c["ay_max"], mp_c["a_min"])
+            if best is None or mi["kernel_ms"] < best["kernel_ms"]:
+                best = mi
+        t0 = time.perf_counter()
+        xo, io = port.map_speed_profile(port.construct_waypoints(trk), spc, mp_c["ay_max"], mp_c["a_min"])
+        cpu_s = time.perf_counter() - t0
+        map_line = {"track": args.track, "waypoints": int(xg.shape[0]), "ctas": best["ctas"], "status": best["status_str"],
+                    "admm_iterations": best["iters"], "kernel_ms": best["kernel_ms"],
+                    "us_per_iteration": 1e3 * best["kernel_ms"] / max(best["iters"], 1),
+                    "cpu_port_s": cpu_s, "cpu_iterations": int(io.iter), "max_abs_diff_m_s": float(np.abs(xo - xg).max()),
+                    "api": "acmpc_track_speed_profile_host (construct_waypoints + compute_map_speed_profile, "
+                           "spatial_mpc.py:60-87,125-154)"}
+
     line = {
         "metric": METRIC, "value": world * B * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": max(W, 3), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -377,7 +400,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                         "oracle's C port without the reference's ~6 ms of Python glue per call",
         "iters_mean": [float(iters[:, 0].mean()), float(iters[:, 1].mean())],
         "solved_frac": solved, "device_equals_host_path": bool(same),
-        "launch": mpc.launch_info(), "clocks": clocks,
+        "launch": launch_info, "clocks": clocks, "map_speed_profile": map_line,
     }
     print(json.dumps(line), flush=True)
 
@@ -393,6 +416,7 @@ def main():
                     help="N > 1: where the packed results go at the end of a step (rank 0 / every rank)")
     ap.add_argument("--track", default="monza")
     ap.add_argument("--horizon", type=int, default=50)
+    ap.add_argument("--no-map-profile", action="store_true", help="skip the whole-track speed-profile leg")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall-clock budget of the cpu_baseline leg")
     ap.add_argument("--ref-sample", type=int, default=1024, help="instances per step of --impl reference")
     ap.add_argument("--latency-reps", type=int, default=200)
