@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # ACMPC_B200_LIB: load another build of the same sources (instrumented experiments under tools/)
 LIB_PATH = os.environ.get("ACMPC_B200_LIB") or os.path.join(CSRC, "libacmpc_b200.so")
 _SOURCES = [os.path.join(CSRC, "acmpc_b200.cu"), os.path.join(CSRC, "mpc_warp.cuh"), os.path.join(CSRC, "simt.cuh"),
-            os.path.join(CSRC, "map_profile.cuh"), os.path.join(CSRC, "publish.cuh"),
+            os.path.join(CSRC, "map_profile.cuh"), os.path.join(CSRC, "publish.cuh"), os.path.join(CSRC, "track_prep.cuh"),
             os.path.join(os.path.dirname(_HERE), "include", "acmpc_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -30,6 +30,8 @@ EXPORTED = [
     "acmpc_reference_speeds_host",
     "acmpc_reference_paths_host", "acmpc_publish_host", "acmpc_select_commands_f32_host",
     "acmpc_select_commands_f64_host",
+    "acmpc_remove_near_duplicates_host", "acmpc_smooth_tracks_polyfit_host", "acmpc_centre_tracks_host",
+    "acmpc_extract_paths_device", "acmpc_extract_paths_host",
 ]
 
 RC_NAMES = {0: "ACMPC_OK", 1: "ACMPC_ERR_INVALID", 2: "ACMPC_ERR_CUDA", 3: "ACMPC_ERR_NO_DEVICE"}
@@ -167,6 +169,16 @@ def load() -> C.CDLL:
     L.acmpc_select_commands_f32_host.restype = C.c_int32
     L.acmpc_select_commands_f64_host.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, C.c_int32, dp, ip]
     L.acmpc_select_commands_f64_host.restype = C.c_int32
+    L.acmpc_remove_near_duplicates_host.argtypes = [vp, C.c_int32, dp, C.c_double, dp, ip]
+    L.acmpc_remove_near_duplicates_host.restype = C.c_int32
+    L.acmpc_smooth_tracks_polyfit_host.argtypes = [vp, C.c_int32, ip, dp, C.c_int32, C.c_int32, dp, ip, ip]
+    L.acmpc_smooth_tracks_polyfit_host.restype = C.c_int32
+    L.acmpc_centre_tracks_host.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, C.c_int32, dp, ip]
+    L.acmpc_centre_tracks_host.restype = C.c_int32
+    L.acmpc_extract_paths_device.argtypes = [vp, C.c_int32, vp, C.c_int32, vp, vp, vp, C.c_double, C.c_double, vp, vp]
+    L.acmpc_extract_paths_device.restype = C.c_int32
+    L.acmpc_extract_paths_host.argtypes = [vp, C.c_int32, dp, C.c_int32, ip, dp, dp, C.c_double, C.c_double, dp]
+    L.acmpc_extract_paths_host.restype = C.c_int32
     _lib = L
     return L
 

@@ -12,6 +12,7 @@
 // stages per lane.
 //
 // There is NO CPU path in this library: acmpc_create fails with ACMPC_ERR_NO_DEVICE without a GPU.
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -24,6 +25,7 @@
 #include "mpc_warp.cuh"
 #include "map_profile.cuh"
 #include "publish.cuh"
+#include "track_prep.cuh"
 
 namespace {
 
@@ -1131,6 +1133,13 @@ struct Staged {
         used += (bytes + 255) & ~(size_t)255;
         return d;
     }
+    void* scratch(size_t bytes)
+    {
+        if (rc != ACMPC_OK) return nullptr;
+        void* d = base + used;
+        used += (bytes + 255) & ~(size_t)255;
+        return d;
+    }
     void back(void* dst, const void* d, size_t bytes)
     {
         if (rc != ACMPC_OK || !dst) return;
@@ -1220,6 +1229,115 @@ int32_t acmpc_select_commands_f64_host(acmpc_handle* h, int32_t B, int32_t n, co
                                        const double* elapsed, int32_t mode, double* out, int32_t* indices)
 {
     return select_commands<double>(h, B, n, cum_time, commands, elapsed, mode, out, indices);
+}
+
+// ---- track side of the step: track_prep.cuh ---------------------------------------
+
+int32_t acmpc_remove_near_duplicates_host(acmpc_handle* h, int32_t M, const double* xy, double tol, double* out, int32_t* kept)
+{
+    if (!h || M < 0 || !kept || (M > 0 && (!xy || !out))) return ACMPC_ERR_INVALID;
+    if (M == 0) {
+        *kept = 0;
+        return ACMPC_OK;
+    }
+    const int ctas = (M + acmpc::trk::kDupThreads - 1) / acmpc::trk::kDupThreads;
+    const size_t b = (size_t)M * 2 * 8;
+    Staged s(h, 2 * b + (size_t)ctas * 4 + 4 * 256);
+    const double* d_in = (const double*)s.in(xy, b);
+    double* d_out = (double*)s.out(out, b);
+    int* d_cnt = (int*)s.scratch((size_t)ctas * 4);
+    int* d_kept = (int*)s.scratch(4);
+    if (s.rc == ACMPC_OK) {
+        acmpc::trk::near_duplicate_count_kernel<<<ctas, acmpc::trk::kDupThreads, 0, h->stream>>>(d_in, M, tol, d_cnt);
+        acmpc::trk::near_duplicate_scatter_kernel<<<ctas, acmpc::trk::kDupThreads, 0, h->stream>>>(d_in, M, tol, d_cnt, d_out, d_kept);
+    }
+    s.back(kept, d_kept, 4);
+    s.back(out, d_out, b);     // rows [kept, M) of `out` are unspecified
+    return s.finish(2, acmpc::trk::kDupThreads);
+}
+
+static int32_t polyfit_tracks(acmpc_handle* h, int32_t B, const int32_t* offsets, const double* points, const double* points_b,
+                              int32_t num_points, int32_t degree, int32_t pad_origin, double* out, int32_t* status,
+                              int32_t* start_index)
+{
+    if (!h || B < 1 || !offsets || num_points < 1 || degree < 0 || degree > acmpc::trk::kMaxDegree || !out) return ACMPC_ERR_INVALID;
+    if (offsets[0] != 0) return ACMPC_ERR_INVALID;
+    for (int b = 0; b < B; ++b)
+        if (offsets[b + 1] < offsets[b]) return ACMPC_ERR_INVALID;
+    const size_t total = (size_t)offsets[B];
+    if (total > 0 && !points) return ACMPC_ERR_INVALID;
+    const size_t in_b = total * 2 * 8, out_b = (size_t)B * num_points * 2 * 8;
+    Staged s(h, (points_b ? 3 : 1) * in_b + out_b + (size_t)(3 * B + 1) * 4 + 8 * 256);
+    const int* d_off = (const int*)s.in(offsets, (size_t)(B + 1) * 4);
+    const double* d_pts = total ? (const double*)s.in(points, in_b) : nullptr;
+    int launches = 1;
+    if (points_b && total) {                       // centre track: the fit runs on (points + points_b) / 2
+        const double* d_b = (const double*)s.in(points_b, in_b);
+        double* d_mid = (double*)s.scratch(in_b);
+        if (s.rc == ACMPC_OK)
+            acmpc::trk::midline_kernel<<<(unsigned)((total * 2 + 255) / 256), 256, 0, h->stream>>>(d_pts, d_b, total * 2, d_mid);
+        d_pts = d_mid, ++launches;
+    }
+    double* d_out = (double*)s.out(out, out_b);
+    int* d_st = (int*)s.out(status, (size_t)B * 4);
+    int* d_si = (int*)s.out(start_index, (size_t)B * 4);
+    if (s.rc == ACMPC_OK)
+        acmpc::trk::polyfit_resample_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(d_pts, d_off, B, num_points, degree, pad_origin,
+                                                                               d_out, d_st, d_si);
+    s.back(out, d_out, out_b);
+    s.back(status, d_st, (size_t)B * 4);
+    s.back(start_index, d_si, (size_t)B * 4);
+    return s.finish(launches, 128);
+}
+
+int32_t acmpc_smooth_tracks_polyfit_host(acmpc_handle* h, int32_t B, const int32_t* offsets, const double* points,
+                                         int32_t num_points, int32_t degree, double* out, int32_t* status, int32_t* start_index)
+{
+    return polyfit_tracks(h, B, offsets, points, nullptr, num_points, degree, 0, out, status, start_index);
+}
+
+int32_t acmpc_centre_tracks_host(acmpc_handle* h, int32_t B, int32_t N, const double* left, const double* right,
+                                 int32_t num_points, double* centre, int32_t* status)
+{
+    if (!h || B < 1 || N < 1 || !left || !right) return ACMPC_ERR_INVALID;
+    std::vector<int32_t> off((size_t)B + 1);
+    for (int b = 0; b <= B; ++b) off[b] = b * N;
+    // tracks.py:247-252: 10 origin points (x of the first centre point, y = 0) in front, degree 2
+    return polyfit_tracks(h, B, off.data(), left, right, num_points, 2, 10, centre, status, nullptr);
+}
+
+int32_t acmpc_extract_paths_device(acmpc_handle* h, int32_t M, const double* d_centreline, int32_t B, const int32_t* d_index,
+                                   const double* d_offset_lat, const double* d_offset_psi, double lookahead, double ds,
+                                   double* d_paths, void* stream)
+{
+    if (!h || M < 2 || B < 1 || !d_centreline || !d_index || !d_paths || !(ds > 0.0) || !(lookahead >= 0.0)) return ACMPC_ERR_INVALID;
+    if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    const int H = h->cfg.horizon;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    acmpc::trk::extract_paths_kernel<<<(B * H + 127) / 128, 128, 0, st>>>(d_centreline, M, d_index, d_offset_lat, d_offset_psi, B,
+                                                                        H, lookahead, ds, d_paths);
+    if (fail(h, cudaGetLastError(), "extract_paths_kernel")) return ACMPC_ERR_CUDA;
+    return ACMPC_OK;
+}
+
+int32_t acmpc_extract_paths_host(acmpc_handle* h, int32_t M, const double* centreline, int32_t B, const int32_t* index,
+                                 const double* offset_lat, const double* offset_psi, double lookahead, double ds, double* paths)
+{
+    if (!h || M < 2 || B < 1 || !centreline || !index || !paths) return ACMPC_ERR_INVALID;
+    const int H = h->cfg.horizon;
+    const size_t out_b = (size_t)B * H * 3 * 8;
+    Staged s(h, (size_t)M * 16 + (size_t)B * 20 + out_b + 8 * 256);
+    const double* d_cl = (const double*)s.in(centreline, (size_t)M * 16);
+    const int* d_i = (const int*)s.in(index, (size_t)B * 4);
+    const double* d_l = (const double*)s.in(offset_lat, (size_t)B * 8);
+    const double* d_p = (const double*)s.in(offset_psi, (size_t)B * 8);
+    double* d_out = (double*)s.out(paths, out_b);
+    if (s.rc == ACMPC_OK) {
+        const int32_t rc = acmpc_extract_paths_device(h, M, d_cl, B, d_i, d_l, d_p, lookahead, ds, d_out, nullptr);
+        if (rc != ACMPC_OK) return rc;
+    }
+    s.back(paths, d_out, out_b);
+    return s.finish(1, 128);
 }
 
 }  // extern "C"

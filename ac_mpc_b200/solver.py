@@ -252,6 +252,89 @@ class BatchedMPC:
                        idx.ctypes.data_as(C.POINTER(C.c_int32))))
         return (out, idx) if return_indices else out
 
+    # -- track side of the step ---------------------------------
+    def remove_near_duplicate_points(self, track, tol: float = 0.0001) -> np.ndarray:
+        """utils/load.py:30-35 on the device: (M,2) -> the rows farther than `tol` from their predecessor."""
+        t = np.ascontiguousarray(track, dtype=np.float64)
+        if t.ndim != 2 or t.shape[1] != 2:
+            raise ValueError(f"track must be (M, 2), got {t.shape}")
+        out, kept = np.empty_like(t), C.c_int32(0)
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_remove_near_duplicates_host(self._handle(), t.shape[0], t.ctypes.data_as(dp), float(tol),
+                                                                out.ctypes.data_as(dp), C.byref(kept)))
+        return out[:kept.value].copy()
+
+    def smooth_tracks_with_polyfit(self, tracks, num_points: int, degree: int = 3, return_info: bool = False):
+        """perception/utils.py:107-119 for a list of (m_b, 2) tracks (ragged; empty tracks allowed) ->
+        (B, num_points, 2).  return_info adds (status[B], start_index[B])."""
+        tracks = [np.asarray(t, dtype=np.float64).reshape(-1, 2) for t in tracks]
+        B = len(tracks)
+        off = np.zeros(B + 1, np.int32)
+        off[1:] = np.cumsum([t.shape[0] for t in tracks])
+        pts = np.ascontiguousarray(np.concatenate(tracks, axis=0)) if off[-1] else np.zeros((0, 2))
+        out = np.empty((B, int(num_points), 2))
+        st, si = np.empty(B, np.int32), np.empty(B, np.int32)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        self._check(self._lib.acmpc_smooth_tracks_polyfit_host(
+            self._handle(), B, off.ctypes.data_as(ip), pts.ctypes.data_as(dp) if off[-1] else None, int(num_points),
+            int(degree), out.ctypes.data_as(dp), st.ctypes.data_as(ip), si.ctypes.data_as(ip)))
+        return (out, st, si) if return_info else out
+
+    def centre_tracks(self, left, right, num_points: Optional[int] = None) -> np.ndarray:
+        """TrackLimitPerception._calculate_centre_track (perception/tracks.py:247-252) for B frames:
+        left / right (B,N,2) -> (B,num_points,2) (num_points defaults to N = n_polyfit_points)."""
+        left = np.ascontiguousarray(left, dtype=np.float64)
+        right = np.ascontiguousarray(right, dtype=np.float64)
+        if left.ndim != 3 or left.shape != right.shape or left.shape[2] != 2:
+            raise ValueError("left and right must both be (B, N, 2)")
+        B, N = left.shape[:2]
+        num_points = N if num_points is None else int(num_points)
+        out = np.empty((B, num_points, 2))
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_centre_tracks_host(self._handle(), B, N, left.ctypes.data_as(dp), right.ctypes.data_as(dp),
+                                                       num_points, out.ctypes.data_as(dp), None))
+        return out
+
+    def extract_paths(self, centreline, indices, offset_lat=None, offset_psi=None, lookahead: float = 100.0,
+                      ds: float = 0.5) -> np.ndarray:
+        """SURVEY.md section 8d instances from a map centre line (M,2), host buffers: -> (B,H,3)."""
+        cl = np.ascontiguousarray(centreline, dtype=np.float64)
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        B = idx.shape[0]
+        lat = None if offset_lat is None else np.ascontiguousarray(offset_lat, dtype=np.float64)
+        psi = None if offset_psi is None else np.ascontiguousarray(offset_psi, dtype=np.float64)
+        out = np.empty((B, self.H, 3))
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_extract_paths_host(
+            self._handle(), cl.shape[0], cl.ctypes.data_as(dp), B, idx.ctypes.data_as(C.POINTER(C.c_int32)),
+            None if lat is None else lat.ctypes.data_as(dp), None if psi is None else psi.ctypes.data_as(dp),
+            float(lookahead), float(ds), out.ctypes.data_as(dp)))
+        return out
+
+    def extract_paths_device(self, centreline, indices, offset_lat=None, offset_psi=None, lookahead: float = 100.0,
+                             ds: float = 0.5, out=None, stream=None):
+        """Same with DEVICE tensors (centreline (M,2) f64, indices (B,) int32, offsets (B,) f64), asynchronous on
+        `stream`; the (B,H,3) result feeds solve_device without touching the host."""
+        import torch
+
+        if not (centreline.is_cuda and centreline.dtype == torch.float64 and centreline.is_contiguous() and
+                centreline.dim() == 2 and centreline.shape[1] == 2):
+            raise ValueError("centreline must be a contiguous (M, 2) float64 CUDA tensor")
+        if not (indices.is_cuda and indices.dtype == torch.int32 and indices.is_contiguous() and indices.dim() == 1):
+            raise ValueError("indices must be a contiguous int32 CUDA tensor")
+        B = indices.shape[0]
+        for a in (offset_lat, offset_psi):
+            if a is not None and not (a.is_cuda and a.dtype == torch.float64 and a.is_contiguous() and a.numel() == B):
+                raise ValueError("offset_lat / offset_psi must be contiguous float64 CUDA tensors of B elements")
+        if out is None:
+            out = torch.empty((B, self.H, 3), dtype=torch.float64, device=centreline.device)
+        s = torch.cuda.current_stream(centreline.device) if stream is None else stream
+        self._check(self._lib.acmpc_extract_paths_device(
+            self._handle(), centreline.shape[0], centreline.data_ptr(), B, indices.data_ptr(),
+            None if offset_lat is None else offset_lat.data_ptr(), None if offset_psi is None else offset_psi.data_ptr(),
+            float(lookahead), float(ds), out.data_ptr(), C.c_void_p(s.cuda_stream)))
+        return out
+
     # -- device buffers -------------------------------------------------------------------------
     def alloc_device_outputs(self, B: int, fields=None):
         """One packed uint8 CUDA tensor with a 256-byte aligned slab per field (so a multi-GPU run

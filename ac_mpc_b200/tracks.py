@@ -98,6 +98,19 @@ def synthetic_centreline(track: str, ds: float = 0.5, min_radius: float = 15.0) 
     return _resample_closed(xy, ds)
 
 
+def centreline(track: str, map_dir: str | None = None, ds: float = 0.5) -> np.ndarray:
+    """The centre line the benchmark and the sweeps run on: the downloaded map (data/maps/<track>*.npy in the
+    reference's on-disk format, utils/load.py:9-35; resampled to `ds` metres) when `map_dir` holds one, else the
+    synthetic loop of the named length."""
+    if map_dir:
+        from .utils import load
+
+        path = load.find_map(track, map_dir)
+        if path:
+            return _resample_closed(load.track_map(path)["centre"], ds)
+    return synthetic_centreline(track, ds)
+
+
 def make_instances(centreline: np.ndarray, indices, horizon: int, offset_lat=None, offset_psi=None,
                    lookahead: float = 100.0, ds: float = 0.5) -> np.ndarray:
     """(B, H, 3) get_control inputs: ego pose = centreline point i displaced `offset_lat` along the

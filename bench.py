@@ -363,6 +363,44 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                     "api": "acmpc_track_speed_profile_host (construct_waypoints + compute_map_speed_profile, "
                            "spatial_mpc.py:60-87,125-154)"}
 
+    # track sweep (scope row 8f-4): the centre line stays resident, a step uploads (index, lateral offset, heading
+    # offset, v_max) = 28 bytes per instance, the paths are built on the device (acmpc_extract_paths_device) and only
+    # controls + status come back.  Same instances as the timed steps (perturbed_batch's draws).  Outside the timed steps.
+    sweep_line = None
+    if not args.no_sweep:
+        cl_s = tracks.synthetic_centreline(args.track)
+        rng = np.random.default_rng(1 + rank)
+        s_idx = rng.integers(0, cl_s.shape[0], B).astype(np.int32)
+        s_lat, s_psi, s_vmax = rng.uniform(-2.0, 2.0, B), rng.uniform(-0.1, 0.1, B), rng.uniform(20.0, 84.0, B)
+        h_in = [torch.from_numpy(a).pin_memory() for a in (s_idx, s_lat, s_psi, s_vmax)]
+        d_in = [torch.empty_like(a, device=dev) for a in h_in]
+        d_cl = torch.from_numpy(cl_s).to(dev)
+        d_sp = torch.empty((B, H, 3), dtype=torch.float64, device=dev)
+        _, sv = mpc.alloc_device_outputs(B, ["controls", "status"])
+        h_ctl = torch.empty((B, 2, H - 1), dtype=torch.float64).pin_memory()
+        h_st = torch.empty(B, dtype=torch.int32).pin_memory()
+
+        def sweep_step():
+            for d_a, h_a in zip(d_in, h_in):
+                d_a.copy_(h_a, non_blocking=True)
+            mpc.extract_paths_device(d_cl, d_in[0], d_in[1], d_in[2], out=d_sp)
+            mpc.solve_device(d_sp, None, d_in[3], False, out=sv)
+            h_ctl.copy_(sv["controls"], non_blocking=True)
+            h_st.copy_(sv["status"], non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(3):
+            sweep_step()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            sweep_step()
+        sweep_s = time.perf_counter() - t0
+        sweep_line = {"value": B * K / sweep_s, "unit": UNIT, "h2d_bytes_per_step": B * 28,
+                      "d2h_bytes_per_step": B * (2 * (H - 1) * 8 + 4),
+                      "max_abs_path_diff_m": float(np.abs(d_sp.cpu().numpy() - paths).max()),
+                      "controls_equal_timed_steps": bool(np.abs(h_ctl.numpy() - h_out["controls"]).max() < 1e-3),
+                      "api": "acmpc_extract_paths_device -> acmpc_solve_batch_device, centre line resident in HBM"}
+
     line = {
         "metric": METRIC, "value": world * B * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": max(W, 3), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -400,7 +438,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                         "oracle's C port without the reference's ~6 ms of Python glue per call",
         "iters_mean": [float(iters[:, 0].mean()), float(iters[:, 1].mean())],
         "solved_frac": solved, "device_equals_host_path": bool(same),
-        "launch": launch_info, "clocks": clocks, "map_speed_profile": map_line,
+        "launch": launch_info, "clocks": clocks, "map_speed_profile": map_line, "track_sweep": sweep_line,
     }
     print(json.dumps(line), flush=True)
 
@@ -416,6 +454,7 @@ def main():
                     help="N > 1: where the packed results go at the end of a step (rank 0 / every rank)")
     ap.add_argument("--track", default="monza")
     ap.add_argument("--horizon", type=int, default=50)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the device-resident track-sweep leg")
     ap.add_argument("--no-map-profile", action="store_true", help="skip the whole-track speed-profile leg")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="wall-clock budget of the cpu_baseline leg")
     ap.add_argument("--ref-sample", type=int, default=1024, help="instances per step of --impl reference")

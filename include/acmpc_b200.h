@@ -221,6 +221,43 @@ int32_t acmpc_select_commands_f64_host(acmpc_handle *h, int32_t B, int32_t n, co
                                        const double *commands, const double *elapsed, int32_t mode, double *out,
                                        int32_t *indices);
 
+/* ---- Track side of the step ---------------------------------------------------
+ * utils/load.py:30-35 remove_near_duplicate_points: keeps row 0 and every row whose distance to its predecessor IN THE
+ * INPUT exceeds tol (the reference uses 0.0001), order preserved.  xy[M,2] -> out[*kept,2]; `out` needs room for M rows. */
+int32_t acmpc_remove_near_duplicates_host(acmpc_handle *h, int32_t M, const double *xy, double tol, double *out,
+                                          int32_t *kept);
+
+/* perception/utils.py:107-119 smooth_track_with_polyfit(track, num_points, degree) for B tracks at once.
+ * Track b = rows offsets[b] .. offsets[b+1] of points[.,2] (x, y); offsets[0] == 0; an empty track yields the
+ * reference's stub line.  out[B,num_points,2].  degree 0..3 (the reference uses 2 and 3).
+ * status[B] (may be NULL): 0 fitted, 1 empty track, 2 fewer than degree+1 distinct abscissae (numpy: RankWarning and the
+ * minimum-norm solution; here: the highest degree the data determine).  start_index[B] (may be NULL) = the argmin of
+ * perception/utils.py:116 on the 500-point scan. */
+#define ACMPC_TRACK_OK 0
+#define ACMPC_TRACK_EMPTY 1
+#define ACMPC_TRACK_RANK_DEFICIENT 2
+int32_t acmpc_smooth_tracks_polyfit_host(acmpc_handle *h, int32_t B, const int32_t *offsets, const double *points,
+                                         int32_t num_points, int32_t degree, double *out, int32_t *status,
+                                         int32_t *start_index);
+
+/* perception/tracks.py:247-252 TrackLimitPerception._calculate_centre_track for B frames: left/right [B,N,2] (the
+ * smoothed limits) -> centre [B,num_points,2] = degree-2 fit of (left + right) / 2 with 10 origin points in front. */
+int32_t acmpc_centre_tracks_host(acmpc_handle *h, int32_t B, int32_t N, const double *left, const double *right,
+                                 int32_t num_points, double *centre, int32_t *status);
+
+/* SURVEY.md section 8d "instance -> get_control input" on the device: centre line [M,2] (closed loop, one point every
+ * ds metres), per instance a map index, a lateral offset along the left normal and a heading offset ->
+ * paths[B,H,3] = the next `lookahead` metres resampled to H points in the ego frame (x right, y forward,
+ * spatial_mpc.py:186-187) + widths linspace(10, 6, H) (controller.py:264) -- the layout acmpc_solve_batch_device
+ * reads.  d_offset_lat / d_offset_psi may be NULL (= 0).  _device: device pointers, asynchronous on `stream`
+ * (NULL = the handle's stream), no synchronisation. */
+int32_t acmpc_extract_paths_device(acmpc_handle *h, int32_t M, const double *d_centreline, int32_t B,
+                                   const int32_t *d_index, const double *d_offset_lat, const double *d_offset_psi,
+                                   double lookahead, double ds, double *d_paths, void *stream);
+int32_t acmpc_extract_paths_host(acmpc_handle *h, int32_t M, const double *centreline, int32_t B, const int32_t *index,
+                                 const double *offset_lat, const double *offset_psi, double lookahead, double ds,
+                                 double *paths);
+
 #ifdef __cplusplus
 }
 #endif
