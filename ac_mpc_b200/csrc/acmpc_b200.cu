@@ -1313,9 +1313,11 @@ int32_t acmpc_extract_paths_device(acmpc_handle* h, int32_t M, const double* d_c
     if (!h || M < 2 || B < 1 || !d_centreline || !d_index || !d_paths || !(ds > 0.0) || !(lookahead >= 0.0)) return ACMPC_ERR_INVALID;
     if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
     const int H = h->cfg.horizon;
-    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);   // as acmpc_solve_batch_device: NULL = the legacy default stream
+    const double div = H > 1 ? (double)(H - 1) : 1.0;
     acmpc::trk::extract_paths_kernel<<<(B * H + 127) / 128, 128, 0, st>>>(d_centreline, M, d_index, d_offset_lat, d_offset_psi, B,
-                                                                        H, lookahead, ds, d_paths);
+                                                                        H, lookahead, ds, lookahead / div, (6.0 - 10.0) / div,
+                                                                        d_paths);
     if (fail(h, cudaGetLastError(), "extract_paths_kernel")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
 }
@@ -1333,7 +1335,7 @@ int32_t acmpc_extract_paths_host(acmpc_handle* h, int32_t M, const double* centr
     const double* d_p = (const double*)s.in(offset_psi, (size_t)B * 8);
     double* d_out = (double*)s.out(paths, out_b);
     if (s.rc == ACMPC_OK) {
-        const int32_t rc = acmpc_extract_paths_device(h, M, d_cl, B, d_i, d_l, d_p, lookahead, ds, d_out, nullptr);
+        const int32_t rc = acmpc_extract_paths_device(h, M, d_cl, B, d_i, d_l, d_p, lookahead, ds, d_out, h->stream);
         if (rc != ACMPC_OK) return rc;
     }
     s.back(paths, d_out, out_b);

@@ -210,8 +210,9 @@ __global__ void midline_kernel(const double* __restrict__ left, const double* __
 // One thread per output point (b, k).  centreline [M, 2] closed loop sampled every `ds` metres.
 __global__ void extract_paths_kernel(const double* __restrict__ cl, int M, const int* __restrict__ index,
                                      const double* __restrict__ offset_lat, const double* __restrict__ offset_psi, int B,
-                                     int H, double lookahead, double ds, double* __restrict__ paths)
-{
+                                     int H, double lookahead, double ds, double step_s, double step_w,
+                                     double* __restrict__ paths)
+{   // step_s = lookahead / (H - 1), step_w = (6 - 10) / (H - 1): the np.linspace steps, divided once on the host
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * H) return;
     const int b = t / H, k = t - b * H;
@@ -219,14 +220,16 @@ __global__ void extract_paths_kernel(const double* __restrict__ cl, int M, const
     if (i < 0) i += M;
     const int i1 = i + 1 == M ? 0 : i + 1;
     const double ox = cl[2 * i], oy = cl[2 * i + 1];
-    const double th = atan2(cl[2 * i1 + 1] - oy, cl[2 * i1] - ox);
-    double sn, cs;
-    sincos(th, &sn, &cs);
+    // (cos, sin) of the tangent heading th = atan2(ty, tx) is the normalised tangent itself; th + psi by the angle
+    // addition formulas -- no atan2 and one small-argument sincos per thread instead of atan2 + two sincos
+    const double tx = cl[2 * i1] - ox, ty = cl[2 * i1 + 1] - oy, rn = 1.0 / sqrt(tx * tx + ty * ty);
+    const double cs = tx * rn, sn = ty * rn;
     const double lat = offset_lat ? offset_lat[b] : 0.0, psi = offset_psi ? offset_psi[b] : 0.0;
     const double gx = ox + lat * -sn, gy = oy + lat * cs;             // ego origin: `lat` metres along the left normal
-    double se, ce;
-    sincos(th + psi, &se, &ce);
-    const double s = linspace_at(0.0, lookahead, H, k) / ds;
+    double sp, cp;
+    sincos(psi, &sp, &cp);
+    const double se = sn * cp + cs * sp, ce = cs * cp - sn * sp;
+    const double s = (k == H - 1 ? lookahead : __dmul_rn((double)k, step_s)) / ds;
     const double fl = floor(s), frac = s - fl;
     int ia = (int)((i + (long long)fl) % M);
     const int ib = ia + 1 == M ? 0 : ia + 1;
@@ -235,7 +238,7 @@ __global__ void extract_paths_kernel(const double* __restrict__ cl, int M, const
     double* o = paths + (size_t)t * 3;
     o[0] = rx * se + ry * -ce;                                        // x right
     o[1] = rx * ce + ry * se;                                         // y forward
-    o[2] = linspace_at(10.0, 6.0, H, k);                              // controller.py:264
+    o[2] = k == H - 1 ? 6.0 : __dadd_rn(__dmul_rn((double)k, step_w), 10.0);   // np.linspace(10, 6, H), controller.py:264
 }
 
 }   // namespace trk

@@ -250,7 +250,7 @@ int32_t acmpc_centre_tracks_host(acmpc_handle *h, int32_t B, int32_t N, const do
  * paths[B,H,3] = the next `lookahead` metres resampled to H points in the ego frame (x right, y forward,
  * spatial_mpc.py:186-187) + widths linspace(10, 6, H) (controller.py:264) -- the layout acmpc_solve_batch_device
  * reads.  d_offset_lat / d_offset_psi may be NULL (= 0).  _device: device pointers, asynchronous on `stream`
- * (NULL = the handle's stream), no synchronisation. */
+ * (the same stream argument as acmpc_solve_batch_device, so the two calls are ordered), no synchronisation. */
 int32_t acmpc_extract_paths_device(acmpc_handle *h, int32_t M, const double *d_centreline, int32_t B,
                                    const int32_t *d_index, const double *d_offset_lat, const double *d_offset_psi,
                                    double lookahead, double ds, double *d_paths, void *stream);
