@@ -1311,13 +1311,22 @@ int32_t acmpc_extract_paths_device(acmpc_handle* h, int32_t M, const double* d_c
                                    double* d_paths, void* stream)
 {
     if (!h || M < 2 || B < 1 || !d_centreline || !d_index || !d_paths || !(ds > 0.0) || !(lookahead >= 0.0)) return ACMPC_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(d_centreline) & 15) {
+        h->err = "centre line must be 16-byte aligned (rows are read as double2)";
+        return ACMPC_ERR_INVALID;
+    }
     if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
     const int H = h->cfg.horizon;
     cudaStream_t st = static_cast<cudaStream_t>(stream);   // as acmpc_solve_batch_device: NULL = the legacy default stream
     const double div = H > 1 ? (double)(H - 1) : 1.0;
-    acmpc::trk::extract_paths_kernel<<<(B * H + 127) / 128, 128, 0, st>>>(d_centreline, M, d_index, d_offset_lat, d_offset_psi, B,
-                                                                        H, lookahead, ds, lookahead / div, (6.0 - 10.0) / div,
-                                                                        d_paths);
+    const size_t smem = (size_t)H * 24 * (1 + acmpc::trk::kExtractThreads / 32);   // step table + one [H,3] tile per warp
+    if (smem > 48 * 1024 &&
+        fail(h, cudaFuncSetAttribute(acmpc::trk::extract_paths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+             "extract_paths_kernel: horizon too long for the shared-memory tiles"))
+        return ACMPC_ERR_CUDA;
+    acmpc::trk::extract_paths_kernel<<<(B + acmpc::trk::kExtractGroup - 1) / acmpc::trk::kExtractGroup, acmpc::trk::kExtractThreads,
+                                       smem, st>>>(d_centreline, M, d_index, d_offset_lat, d_offset_psi, B, H, lookahead, ds,
+                                                   lookahead / div, (6.0 - 10.0) / div, d_paths);
     if (fail(h, cudaGetLastError(), "extract_paths_kernel")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
 }

@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace acmpc {
 namespace trk {
 
@@ -86,21 +88,26 @@ __device__ __forceinline__ double warp_sum(double v)
 struct OrthoFit {
     double a[kMaxDegree + 1], b[kMaxDegree + 1], c[kMaxDegree + 1];   // recurrence (alpha, beta) and coefficients
     int degree;
+    // every loop below is unrolled over the compile-time kMaxDegree so that a / b / c stay in registers
     // p_k(t) for k = 0..degree by p_{k+1} = (t - a_k) p_k - b_k p_{k-1}; returns sum c_k p_k
     __device__ __forceinline__ double eval(double t) const
     {
         double pm = 0.0, p = 1.0, s = c[0];
-        for (int k = 0; k < degree; ++k) {
-            const double pn = (t - a[k]) * p - b[k] * pm;
-            pm = p, p = pn;
-            s += c[k + 1] * p;
-        }
+#pragma unroll
+        for (int k = 0; k < kMaxDegree; ++k)
+            if (k < degree) {
+                const double pn = (t - a[k]) * p - b[k] * pm;
+                pm = p, p = pn;
+                s += c[k + 1] * p;
+            }
         return s;
     }
-    __device__ __forceinline__ double basis(double t, int k) const
+    template <int K>
+    __device__ __forceinline__ double basis(double t) const
     {
         double pm = 0.0, p = 1.0;
-        for (int j = 0; j < k; ++j) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
             const double pn = (t - a[j]) * p - b[j] * pm;
             pm = p, p = pn;
         }
@@ -154,32 +161,47 @@ __global__ void polyfit_resample_kernel(const double* __restrict__ points, const
     double g_prev = 1.0;
     int st = ACMPC_TRACK_OK;
     const double rcond = (double)n * 2.220446049250313e-16;            // np.polyfit: rcond = len(x) * eps
-    for (int k = 0; k <= degree; ++k) {
+    auto pass = [&](auto kc) {                          // one degree: three warp reductions over the track's points
+        constexpr int k = decltype(kc)::value;
+        if (k > degree || st != ACMPC_TRACK_OK) return;     // warp-uniform
         double g = 0.0, gt = 0.0, gf = 0.0, raw = 0.0;
         for (int i = lane; i < n; i += 32) {
-            const double t = py(i), pk = f.basis(t, k);
+            const double t = py(i), pk = f.template basis<k>(t);
             g += pk * pk, gt += t * pk * pk, gf += px(i) * pk;
             double r = 1.0;
+#pragma unroll
             for (int j = 0; j < k; ++j) r *= t * t;
             raw += r;
         }
         g = warp_sum(g), gt = warp_sum(gt), gf = warp_sum(gf), raw = warp_sum(raw);
-        if (k > 0 && !(g > rcond * rcond * raw)) {   // column k lies in the span of the lower ones
+        if (k > 0 && !(g > rcond * rcond * raw)) {          // column k lies in the span of the lower ones
             f.degree = k - 1, st = ACMPC_TRACK_RANK_DEFICIENT;
-            break;
+            return;
         }
         f.c[k] = gf / g, f.a[k] = gt / g;
         f.b[k] = k > 0 ? g / g_prev : 0.0;
         g_prev = g;
-    }
+    };
+    pass(std::integral_constant<int, 0>{});
+    pass(std::integral_constant<int, 1>{});
+    pass(std::integral_constant<int, 2>{});
+    pass(std::integral_constant<int, 3>{});
+    static_assert(kMaxDegree == 3, "one pass per degree");
 
-    // ynew = linspace(0, ymax, 500); start_index = argmin(||(poly(ynew), ynew)||), first minimum
-    double best = INFINITY;
+    // ynew = linspace(0, ymax, 500); start_index = argmin(||(poly(ynew), ynew)||), first minimum.  The comparison is on
+    // sqrt(x^2 + y^2) as numpy rounds it (two samples whose squares differ can share a square root, and argmin then
+    // takes the first), but the square root is only taken for samples whose square is within a few ulp of the lane's
+    // running minimum or below it.
+    const double scan_step = ymax / (double)(kScanPoints - 1);
+    double best = INFINITY, gate = INFINITY;
     int arg = 0x7fffffff;
     for (int j = lane; j < kScanPoints; j += 32) {
-        const double y = linspace_at(0.0, ymax, kScanPoints, j), x = f.eval(y);
-        const double r = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
-        if (r < best) best = r, arg = j;
+        const double y = j == kScanPoints - 1 ? ymax : __dmul_rn((double)j, scan_step);   // linspace: j * step + 0.0
+        const double x = f.eval(y), r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        if (r2 <= gate) {
+            const double r = sqrt(r2);
+            if (r < best) best = r, arg = j, gate = r2 * (1.0 + 0x1p-48);
+        }
     }
     for (int d = 16; d; d >>= 1) {
         const double ob = __shfl_xor_sync(kAll, best, d);
@@ -188,9 +210,11 @@ __global__ void polyfit_resample_kernel(const double* __restrict__ points, const
     }
     if (arg == 0x7fffffff) arg = 0;
     const double y0 = linspace_at(0.0, ymax, kScanPoints, arg);
+    const double out_step = num_points > 1 ? (ymax - y0) / (double)(num_points - 1) : 0.0;
     for (int j = lane; j < num_points; j += 32) {
-        const double y = linspace_at(y0, ymax, num_points, j);
-        o[2 * j] = f.eval(y), o[2 * j + 1] = y;
+        const double y = (out_step == 0.0 || j == num_points - 1) ? linspace_at(y0, ymax, num_points, j)
+                                                                  : __dadd_rn(__dmul_rn((double)j, out_step), y0);
+        reinterpret_cast<double2*>(o)[j] = make_double2(f.eval(y), y);
     }
     if (lane == 0) {
         if (status) status[b] = st;
@@ -207,38 +231,76 @@ __global__ void midline_kernel(const double* __restrict__ left, const double* __
 }
 
 // ---- instance extraction -------------------------------------------------------------------
-// One thread per output point (b, k).  centreline [M, 2] closed loop sampled every `ds` metres.
-__global__ void extract_paths_kernel(const double* __restrict__ cl, int M, const int* __restrict__ index,
-                                     const double* __restrict__ offset_lat, const double* __restrict__ offset_psi, int B,
-                                     int H, double lookahead, double ds, double step_s, double step_w,
-                                     double* __restrict__ paths)
-{   // step_s = lookahead / (H - 1), step_w = (6 - 10) / (H - 1): the np.linspace steps, divided once on the host
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B * H) return;
-    const int b = t / H, k = t - b * H;
-    int i = index[b] % M;
-    if (i < 0) i += M;
-    const int i1 = i + 1 == M ? 0 : i + 1;
-    const double ox = cl[2 * i], oy = cl[2 * i + 1];
-    // (cos, sin) of the tangent heading th = atan2(ty, tx) is the normalised tangent itself; th + psi by the angle
-    // addition formulas -- no atan2 and one small-argument sincos per thread instead of atan2 + two sincos
-    const double tx = cl[2 * i1] - ox, ty = cl[2 * i1 + 1] - oy, rn = 1.0 / sqrt(tx * tx + ty * ty);
-    const double cs = tx * rn, sn = ty * rn;
-    const double lat = offset_lat ? offset_lat[b] : 0.0, psi = offset_psi ? offset_psi[b] : 0.0;
-    const double gx = ox + lat * -sn, gy = oy + lat * cs;             // ego origin: `lat` metres along the left normal
-    double sp, cp;
-    sincos(psi, &sp, &cp);
-    const double se = sn * cp + cs * sp, ce = cs * cp - sn * sp;
-    const double s = (k == H - 1 ? lookahead : __dmul_rn((double)k, step_s)) / ds;
-    const double fl = floor(s), frac = s - fl;
-    int ia = (int)((i + (long long)fl) % M);
-    const int ib = ia + 1 == M ? 0 : ia + 1;
-    const double qx = cl[2 * ia] * (1.0 - frac) + cl[2 * ib] * frac, qy = cl[2 * ia + 1] * (1.0 - frac) + cl[2 * ib + 1] * frac;
-    const double rx = qx - gx, ry = qy - gy;
-    double* o = paths + (size_t)t * 3;
-    o[0] = rx * se + ry * -ce;                                        // x right
-    o[1] = rx * ce + ry * se;                                         // y forward
-    o[2] = k == H - 1 ? 6.0 : __dadd_rn(__dmul_rn((double)k, step_w), 10.0);   // np.linspace(10, 6, H), controller.py:264
+// centreline [M, 2]: closed loop sampled every `ds` metres.  A CTA of kExtractThreads threads builds kExtractGroup
+// instances: the per-step table (map offset, interpolation weight, width -- the same for every instance) and the
+// per-instance ego frames are computed once into shared memory, then every warp walks whole instances, one output point
+// per lane: two gathers from the L2-resident centre line, a 2x2 rotation and 24 contiguous bytes out.  HBM-bound on the
+// [B, H, 3] store.  step_s = lookahead / (H - 1), step_w = (6 - 10) / (H - 1): the np.linspace steps, divided on the host.
+constexpr int kExtractThreads = 256;
+constexpr int kExtractGroup = 32;
+
+struct EgoFrame {
+    double gx, gy, se, ce;    // ego origin, sin / cos of the ego heading
+    int i;                    // map index of the instance
+};
+
+__global__ void __launch_bounds__(kExtractThreads)
+extract_paths_kernel(const double* __restrict__ cl, int M, const int* __restrict__ index,
+                     const double* __restrict__ offset_lat, const double* __restrict__ offset_psi, int B, int H,
+                     double lookahead, double ds, double step_s, double step_w, double* __restrict__ paths)
+{
+    extern __shared__ double smem[];
+    double* frac = smem;                              // [H]
+    double* width = smem + H;                         // [H]
+    int* step = reinterpret_cast<int*>(smem + 2 * H); // [H], already reduced mod M
+    __shared__ EgoFrame frame[kExtractGroup];
+    const int b0 = blockIdx.x * kExtractGroup, nb = min(kExtractGroup, B - b0);
+    for (int k = threadIdx.x; k < H; k += kExtractThreads) {
+        const double s = (k == H - 1 ? lookahead : __dmul_rn((double)k, step_s)) / ds, fl = floor(s);
+        frac[k] = s - fl;
+        step[k] = (int)((long long)fl % M);
+        width[k] = k == H - 1 ? 6.0 : __dadd_rn(__dmul_rn((double)k, step_w), 10.0);   // np.linspace(10, 6, H), controller.py:264
+    }
+    if (threadIdx.x < nb) {
+        const int b = b0 + threadIdx.x;
+        int i = index[b] % M;
+        if (i < 0) i += M;
+        const int i1 = i + 1 == M ? 0 : i + 1;
+        const double ox = cl[2 * i], oy = cl[2 * i + 1];
+        // (cos, sin) of the tangent heading atan2(ty, tx) is the normalised tangent itself; heading + psi by the angle
+        // addition formulas: no atan2, one small-argument sincos
+        const double tx = cl[2 * i1] - ox, ty = cl[2 * i1 + 1] - oy, rn = 1.0 / sqrt(tx * tx + ty * ty);
+        const double cs = tx * rn, sn = ty * rn;
+        const double lat = offset_lat ? offset_lat[b] : 0.0, psi = offset_psi ? offset_psi[b] : 0.0;
+        double sp, cp;
+        sincos(psi, &sp, &cp);
+        EgoFrame f;
+        f.gx = ox + lat * -sn, f.gy = oy + lat * cs;                  // `lat` metres along the left normal
+        f.se = sn * cp + cs * sp, f.ce = cs * cp - sn * sp;
+        f.i = i;
+        frame[threadIdx.x] = f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* tile = smem + 3 * H + (size_t)warp * 3 * H;   // this warp's [H, 3] staging tile (after the table; 2.5 H doubles used)
+    for (int g = warp; g < nb; g += kExtractThreads / 32) {
+        const EgoFrame f = frame[g];
+        for (int k = lane; k < H; k += 32) {
+            int ia = f.i + step[k];
+            if (ia >= M) ia -= M;
+            const int ib = ia + 1 == M ? 0 : ia + 1;
+            const double2 pa = reinterpret_cast<const double2*>(cl)[ia], pb = reinterpret_cast<const double2*>(cl)[ib];
+            const double w = frac[k];
+            const double rx = pa.x * (1.0 - w) + pb.x * w - f.gx, ry = pa.y * (1.0 - w) + pb.y * w - f.gy;
+            tile[3 * k] = rx * f.se + ry * -f.ce;                     // x right
+            tile[3 * k + 1] = rx * f.ce + ry * f.se;                  // y forward
+            tile[3 * k + 2] = width[k];
+        }
+        __syncwarp();
+        double* o = paths + (size_t)(b0 + g) * H * 3;                 // 24 H contiguous bytes, 256 per store instruction
+        for (int e = lane; e < 3 * H; e += 32) o[e] = tile[e];
+        __syncwarp();
+    }
 }
 
 }   // namespace trk
