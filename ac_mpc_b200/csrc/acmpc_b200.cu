@@ -180,8 +180,11 @@ __device__ __forceinline__ acmpc::InstanceOut slice_outputs(const acmpc_outputs&
 // Kernel 1: waypoints + speed-profile QP, one warp per instance, registers only (plus 2 KB of scratch):
 // small code, high occupancy.  Hands the speed profile to kernel 2 through p.vel ([B,n], = out.v_ref when
 // the caller asked for that field).
-template <int C>
-__global__ void __launch_bounds__(32, 12) acmpc_speed_kernel(const __grid_constant__ KernelParams p)
+// OCC = CTAs (= warps) per SM the register allocation aims at: 12 (168 registers) is the faster warp and serves every
+// batch that fits in one wave (and batch 1: 0.217 ms p50 against 0.230 ms); 16 (128 registers, more spills) wins once the
+// batch needs several waves -- 4096 instances at H = 50: 0.1355 ms against 0.1443 ms (launch(), speed_kernel_for()).
+template <int C, int OCC = 12>
+__global__ void __launch_bounds__(32, OCC) acmpc_speed_kernel(const __grid_constant__ KernelParams p)
 {
     // one warp = one CTA: instances need 25..100+ iterations, and a multi-warp CTA would hold its slots until its
     // slowest warp is done
@@ -383,11 +386,12 @@ const void* kernel_for(int H)   // control kernel
     }
 }
 
-const void* speed_kernel_for(int H)
+const void* speed_kernel_for(int H, bool dense = false)
 {
     switch (stages_per_lane(H)) {
         case 1: return reinterpret_cast<const void*>(&acmpc_speed_kernel<1>);
-        case 2: return reinterpret_cast<const void*>(&acmpc_speed_kernel<2>);
+        case 2: return dense ? reinterpret_cast<const void*>(&acmpc_speed_kernel<2, 16>)
+                             : reinterpret_cast<const void*>(&acmpc_speed_kernel<2>);
         case 3: return reinterpret_cast<const void*>(&acmpc_speed_kernel<3>);
         default: return reinterpret_cast<const void*>(&acmpc_speed_kernel<4>);
     }
@@ -465,7 +469,8 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
         if (h->ev_count < kEventRing) ++h->ev_count;
         cudaEventRecord(ev[0], stream);
     }
-    if (fail(h, cudaLaunchKernel(speed_kernel_for(H), dim3(B), dim3(32), args, speed_smem_bytes_for(H), stream),
+    const bool dense = B > 12 * h->sm_count;   // more instances than one wave of the 12-per-SM variant holds
+    if (fail(h, cudaLaunchKernel(speed_kernel_for(H, dense), dim3(B), dim3(32), args, speed_smem_bytes_for(H), stream),
              "speed kernel launch"))
         return ACMPC_ERR_CUDA;
     if (ev) cudaEventRecord(ev[1], stream);
@@ -553,6 +558,9 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
         fail(h, cudaFuncSetAttribute(speed_kernel_for(cfg->horizon), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)speed_smem_bytes_for(cfg->horizon)),
              "cudaFuncSetAttribute(speed)") ||
+        fail(h, cudaFuncSetAttribute(speed_kernel_for(cfg->horizon, true), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)speed_smem_bytes_for(cfg->horizon)),
+             "cudaFuncSetAttribute(speed, dense)") ||
         fail(h, cudaFuncSetAttribute(kernel_for(cfg->horizon), cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared),
              "cudaFuncSetAttribute(carveout)") ||

@@ -18,7 +18,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "ac_mpc_b200", "csrc", "libacmpc_b200.so")
-SRC = os.path.join(ROOT, "ac_mpc_b200", "csrc", "mpc_warp.cuh")
+SRC = os.path.join(ROOT, "ac_mpc_b200", "csrc", os.environ.get("NCU_SUMMARY_SRC", "mpc_warp.cuh"))
 
 RAW = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
@@ -126,7 +126,7 @@ def main():
                 fresh = True
                 reg = "kernel wrapper (acmpc_b200.cu)"
                 for f, l in chain:   # innermost phase-level function of mpc_warp.cuh
-                    if f == "mpc_warp.cuh":
+                    if f == os.path.basename(SRC):
                         k = bisect.bisect_right(starts, l) - 1
                         name = marks[k][1] if k >= 0 else "?"
                         if "::" in name or name in ("build_waypoints", "speed_instance", "control_instance"):
@@ -140,7 +140,7 @@ def main():
         print(f"{tot[0]} warp instructions executed, {tot[1]} stall samples, {tot[3]} static SASS instructions. "
               "Attribution: each SASS instruction goes to the innermost SpeedQP / ControlQP method (or phase function) "
               "of its `-lineinfo` inline chain, helpers (shuffles, selects, 3x3 products) included.\n")
-        print("| function (mpc_warp.cuh) | executed instr. | stall samples | no_instruction samples | static instr. |\n|---|---|---|---|---|")
+        print(f"| function ({os.path.basename(SRC)}) | executed instr. | stall samples | no_instruction samples | static instr. |\n|---|---|---|---|---|")
         for reg, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             if a[0] / tot[0] < 0.004:
                 continue
