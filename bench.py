@@ -8,8 +8,12 @@
 A "step" is one pass of the hot path (SpatialMPC.get_control: waypoints + speed-profile QP +
 linearise/assemble + control QP + unpack/rollout/cost) over one batch of synthetic instances:
 BASELINE.json configs[1] = Monza racing block (H = 50), 4096 perturbed initial states per GPU.
-At N > 1 every rank solves its own 4096-instance shard (weak scaling, no data-path collective) and the
-step ends with the single NCCL collective that brings the packed outputs to rank 0 (--collective all_gather: to every rank).
+At N > 1 every rank solves its own 4096-instance shard (weak scaling, no data-path collective) and every
+step has the single NCCL collective that brings the packed outputs to rank 0 (--collective all_gather: to every rank).
+By default (--gather pipelined) the collective of step i runs on a side stream while step i + 1 computes, from the
+other of two output buffers; it starts after the start event of the step it overlaps and ends before that step's end
+event, and the collective of the last step is a timed region of its own -- all K collectives are inside the timed time.
+--gather in_step keeps each collective inside its own step.
 
 One JSON line on stdout (rank 0).  `value` = device-timed throughput with inputs resident in HBM;
 `e2e` = the same metric through the reference-facing API (SpatialMPC.get_control_batch -> C ABI host
@@ -245,18 +249,54 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     mpc.set_profiling(True)        # events around each of the two kernels, on the launching stream
-    for i in range(K):
-        flush.fill_(i & 0xFF)                  # L2 flush between timed iterations (outside the events)
-        ev[i][0].record()
-        kev[i][0].record()
-        mpc.solve_device(d_paths, None, d_vmax, False, out=views)
-        kev[i][1].record()
-        if world > 1:
-            collect()
-        ev[i][1].record()
+    pipelined = world > 1 and args.gather == "pipelined"
+    if pipelined:
+        # The gather of step i runs on a side stream WHILE step i + 1 computes (double-buffered outputs): every gather
+        # starts after the start event of the step it overlaps and ends before that step's end event, so nothing
+        # timed hides in an L2 flush; the gather of the last step gets a timed region of its own (ev[K]).
+        main, side = torch.cuda.current_stream(), torch.cuda.Stream(device=dev)
+        bufs = [(packed, views), mpc.alloc_device_outputs(B, BENCH_FIELDS)]
+        solved = [torch.cuda.Event() for _ in range(2)]
+
+        def gather_async(buf, after):
+            side.wait_event(after)
+            side.wait_event(solved[buf])
+            with torch.cuda.stream(side):
+                if args.collective == "gather":
+                    dist.gather(bufs[buf][0], slots, dst=0)
+                else:
+                    dist.all_gather_into_tensor(gathered, bufs[buf][0])
+
+        for i in range(K):
+            flush.fill_(i & 0xFF)                  # L2 flush between timed iterations (outside the events)
+            ev[i][0].record()
+            if i > 0:
+                gather_async((i - 1) & 1, ev[i][0])
+            kev[i][0].record()
+            mpc.solve_device(d_paths, None, d_vmax, False, out=bufs[i & 1][1])
+            kev[i][1].record()
+            solved[i & 1].record()
+            main.wait_stream(side)                 # the step ends when its kernels AND the overlapped gather are done
+            ev[i][1].record()
+        ev[K][0].record()
+        gather_async((K - 1) & 1, ev[K][0])
+        main.wait_stream(side)
+        ev[K][1].record()
+        views = bufs[(K - 1) & 1][1]
+    else:
+        for i in range(K):
+            flush.fill_(i & 0xFF)                  # L2 flush between timed iterations (outside the events)
+            ev[i][0].record()
+            kev[i][0].record()
+            mpc.solve_device(d_paths, None, d_vmax, False, out=views)
+            kev[i][1].record()
+            if world > 1:
+                collect()
+            ev[i][1].record()
+        ev.pop()
     torch.cuda.synchronize()
     per_kernel = mpc.collect_kernel_ms()
     mpc.set_profiling(False)
@@ -409,7 +449,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                                "(BASELINE configs[1]), cold start per instance",
                    "track": args.track, "horizon": H, "batch_per_gpu": B, "global_batch": world * B,
                    "l2": "flushed between timed steps (256 MiB fill outside the events)",
-                   "parallelism": f"instances sharded over {world} GPU(s), one final NCCL {args.collective}" if world > 1
+                   "parallelism": f"instances sharded over {world} GPU(s), one final NCCL {args.collective} per step ({args.gather})" if world > 1
                    else "single GPU", "osqp": "eps_abs=eps_rel=1e-3, check 25, adaptive rho interval 50"},
         "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * bin_,
                 "d2h_bytes_per_step": B * bout, "api": "SpatialMPC.get_control_batch -> acmpc_solve_batch_host"},
@@ -450,6 +490,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU per step")
+    ap.add_argument("--gather", default="pipelined", choices=["pipelined", "in_step"],
+                    help="N > 1: the final collective of step i overlaps the kernels of step i + 1 (side stream, double-"
+                         "buffered outputs; the last one is timed on its own) / runs inside its own step")
     ap.add_argument("--collective", default="gather", choices=["gather", "all_gather"],
                     help="N > 1: where the packed results go at the end of a step (rank 0 / every rank)")
     ap.add_argument("--track", default="monza")
