@@ -781,7 +781,13 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
     // (a 1 M-instance sweep would otherwise wait for a 300 MB H2D before its first kernel)
     int chunks = B >= 2048 ? 4 : (B >= 512 ? 2 : 1);
     if (B > 4 * 16384) chunks = (B + 16383) / 16384;
-    const int per = ((B + chunks - 1) / chunks + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
+    int per = ((B + chunks - 1) / chunks + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
+    // experiment switch: instances per chunk.  At 4096 (r1q): 4 x 1024 = 5.50 M solves/s end to end; 1184 (one full wave of
+    // the control kernel) + a 544 tail 5.34 M; 1216 5.27 M; 1100 5.27 M; 896 (5 chunks) 4.99 M
+    if (const char* e = getenv("ACMPC_CHUNK_PER")) {
+        const int v = atoi(e) / kWarpsPerCta * kWarpsPerCta;
+        if (v >= kWarpsPerCta && chunks > 1) per = v, chunks = (B + per - 1) / per;
+    }
     if (h->d_warm && chunks > 1 &&
         fail(h, cudaStreamSynchronize(h->streams[0]), "cudaStreamSynchronize"))   // the zero-fill of new records
         return ACMPC_ERR_CUDA;
