@@ -16,6 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("ACMPC_B200_LIB") or os.path.join(CSRC, "libacmpc_b200.so")
 _SOURCES = [os.path.join(CSRC, "acmpc_b200.cu"), os.path.join(CSRC, "mpc_warp.cuh"), os.path.join(CSRC, "simt.cuh"),
             os.path.join(CSRC, "map_profile.cuh"), os.path.join(CSRC, "publish.cuh"), os.path.join(CSRC, "track_prep.cuh"),
+            os.path.join(CSRC, "model.cuh"),
             os.path.join(os.path.dirname(_HERE), "include", "acmpc_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -32,6 +33,8 @@ EXPORTED = [
     "acmpc_select_commands_f64_host",
     "acmpc_remove_near_duplicates_host", "acmpc_smooth_tracks_polyfit_host", "acmpc_centre_tracks_host",
     "acmpc_extract_paths_device", "acmpc_extract_paths_host",
+    "acmpc_speed_profile_batch_device", "acmpc_speed_profile_batch_host", "acmpc_t2s_host", "acmpc_s2t_host",
+    "acmpc_linearise_host", "acmpc_remove_near_duplicates_cols_host",
 ]
 
 RC_NAMES = {0: "ACMPC_OK", 1: "ACMPC_ERR_INVALID", 2: "ACMPC_ERR_CUDA", 3: "ACMPC_ERR_NO_DEVICE"}
@@ -59,6 +62,7 @@ class Config(C.Structure):
         ("adaptive_rho_tolerance", C.c_double),
         ("scaling", C.c_int32), ("check_termination", C.c_int32),
         ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32),
+        ("check_dualgap", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -71,7 +75,7 @@ class MapInfo(C.Structure):
 
 
 OUTPUT_FIELDS = ["controls", "prediction", "cum_time", "states", "v_ref", "cost", "pri_res", "dua_res",
-                 "status", "status_speed", "iters", "rho_updates", "waypoints"]
+                 "status", "status_speed", "iters", "rho_updates", "waypoints", "derived"]
 
 
 class Outputs(C.Structure):
@@ -88,7 +92,7 @@ def output_spec(H: int):
         "states": ((H, 3), "float64"), "v_ref": ((n,), "float64"), "cost": ((), "float64"),
         "pri_res": ((), "float64"), "dua_res": ((), "float64"), "status": ((), "int32"),
         "status_speed": ((), "int32"), "iters": ((2,), "int32"), "rho_updates": ((2,), "int32"),
-        "waypoints": ((7, n), "float64"),
+        "waypoints": ((7, n), "float64"), "derived": ((3, n - 1), "float64"),
     }
 
 
@@ -179,6 +183,20 @@ def load() -> C.CDLL:
     L.acmpc_extract_paths_device.restype = C.c_int32
     L.acmpc_extract_paths_host.argtypes = [vp, C.c_int32, dp, C.c_int32, ip, dp, dp, C.c_double, C.c_double, dp]
     L.acmpc_extract_paths_host.restype = C.c_int32
+    L.acmpc_speed_profile_batch_device.argtypes = [vp, C.c_int32, vp, vp, C.c_int32, C.c_int32, C.c_double, vp, C.c_int32,
+                                                   vp, vp, vp, vp, vp]
+    L.acmpc_speed_profile_batch_device.restype = C.c_int32
+    L.acmpc_speed_profile_batch_host.argtypes = [vp, C.c_int32, dp, dp, C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                                 dp, ip, ip, ip]
+    L.acmpc_speed_profile_batch_host.restype = C.c_int32
+    L.acmpc_t2s_host.argtypes = [vp, C.c_int32, dp, dp, dp]
+    L.acmpc_t2s_host.restype = C.c_int32
+    L.acmpc_s2t_host.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, dp]
+    L.acmpc_s2t_host.restype = C.c_int32
+    L.acmpc_linearise_host.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, dp]
+    L.acmpc_linearise_host.restype = C.c_int32
+    L.acmpc_remove_near_duplicates_cols_host.argtypes = [vp, C.c_int32, C.c_int32, dp, C.c_double, dp, ip]
+    L.acmpc_remove_near_duplicates_cols_host.restype = C.c_int32
     _lib = L
     return L
 

@@ -12,5 +12,5 @@ def build_mpc(control_config: Dict, vehicle_data, device: int = 0, **osqp_overri
         "max": control_config["speed_profile_constraints"]["v_max"],
         "min": control_config["speed_profile_constraints"]["v_min"],
     }
-    model = SpatialBicycleModel(vehicle_data, velocity_limits)
+    model = SpatialBicycleModel(vehicle_data, velocity_limits, device=device)
     return SpatialMPC(control_config, model, device=device, **osqp_overrides)

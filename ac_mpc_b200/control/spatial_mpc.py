@@ -101,13 +101,12 @@ class SpatialMPC:
             logger.warning("Infeasible problem! reference path:\n" + f"{failed}")
         if status == 1:
             self.projected_control = out["controls"][0].copy()
-            x = out["states"][0][:n]
             self.current_prediction = out["prediction"][0].copy()
             self.reference_path = waypoints
-            self.cum_time = x[:, 2].copy()
-            self.times = np.diff(x[:, 2])
-            self.accelerations = np.diff(x[:, 0]) / self.times      # sic: e_y column, spatial_mpc.py:210
-            self.steer_rates = np.diff(x[:, 1]) / self.times
+            self.cum_time = out["cum_time"][0].copy()
+            # times, accelerations (sic: diff of the e_y column, spatial_mpc.py:210), steer_rates: the kernel's
+            # `derived` rows
+            self.times, self.accelerations, self.steer_rates = (out["derived"][0][k].copy() for k in range(3))
             self.infeasibility_counter = 0
         else:
             logger.warning(f"Infeasible problem! Failed {self.infeasibility_counter} time(s).")
@@ -133,7 +132,31 @@ class SpatialMPC:
             logger.warning("Infeasible problem! reference path:\n" + f"{failed}")
         return reference_path
 
-    def compute_speed_profile(self, reference_path, is_localised: bool = False, end_vel=None):
-        raise NotImplementedError(
-            "stand-alone compute_speed_profile is fused into get_control on the GPU path "
-            "(speed profile = `v_ref` / `waypoints[6]` of the outputs)")
+    def compute_speed_profile(self, reference_path: ReferencePath, is_localised: bool = False,
+                              end_vel=None) -> ReferencePath:
+        """spatial_mpc.py:89-123: the speed-profile QP alone (the speed kernel without the control kernel) on a
+        ReferencePath.  Like the reference it runs on the object's persistent solver (the localised one when
+        `is_localised`), which get_control shares: warm start and carried rho continue across both entry points.
+        Velocities are assigned only when OSQP's status is "solved"."""
+        rows = reference_path.as_array()
+        if rows.shape != (7, self.MPC_horizon - 1):
+            raise ValueError(f"reference path must have {self.MPC_horizon - 1} waypoints (the solver's horizon)")
+        buf = np.ascontiguousarray(rows, dtype=np.float64)[None].copy()
+        res = self._batched().speed_profile_host(buf, np.array([float(self.speed_profile_constraints["v_max"])]),
+                                                 is_localised, end_vel, keep_warm=True)
+        status = int(res["status"][0])
+        self.last_speed_info = dict(status=_capi.STATUS_STRINGS.get(status, str(status)), iters=int(res["iters"][0]),
+                                    rho_updates=int(res["rho_updates"][0]))
+        if status == 1:
+            reference_path.velocities = res["x"][0]
+            self.speed_profile = res["x"][0].copy()
+        else:
+            failed = np.hstack([reference_path.xs, reference_path.ys])
+            logger.warning("Infeasible problem! reference path:\n" + f"{failed}")
+        return reference_path
+
+    def update_prediction(self, spatial_state_prediction: np.ndarray, reference_path: ReferencePath) -> np.ndarray:
+        """spatial_mpc.py:156-168: predicted spatial states (n,3) -> predicted (x, y) locations (n,2) (s2t rollout)."""
+        x = np.ascontiguousarray(spatial_state_prediction, dtype=np.float64)
+        rows = np.ascontiguousarray(reference_path.as_array(), dtype=np.float64)
+        return self._batched().s2t(rows[None], x[None, :, :3], prediction=True)[0]

@@ -26,6 +26,7 @@
 #include "map_profile.cuh"
 #include "publish.cuh"
 #include "track_prep.cuh"
+#include "model.cuh"
 
 namespace {
 
@@ -35,6 +36,7 @@ struct KernelParams {
     const double* offsets;
     const double* vmax;
     double* vel;   // [B,n] speed profile: written by the speed kernel, read by the control kernel
+    double* way;   // NULL, or [B,7,n] ReferencePath rows of the stand-alone speed profile (see speed_instance)
     double* warm;  // NULL or [B, Layout<C>::kWarmDoubles] warm-start records (read when use_warm, always rewritten)
     int32_t use_warm;
     acmpc_outputs out;
@@ -134,6 +136,7 @@ __global__ void acmpc_order_kernel(const double* __restrict__ vmax, int B, doubl
 }
 
 constexpr int kEventRing = 256;
+constexpr int kSlots = 5, kDeviceSlot = 4;
 constexpr int kWarpsPerCta = 4;   // one instance per warp; four warps share one tensor-memory allocation
 
 template <int C>
@@ -174,6 +177,7 @@ __device__ __forceinline__ acmpc::InstanceOut slice_outputs(const acmpc_outputs&
     o.iters = g.iters ? g.iters + (size_t)b * 2 : nullptr;
     o.rho_updates = g.rho_updates ? g.rho_updates + (size_t)b * 2 : nullptr;
     o.waypoints = g.waypoints ? g.waypoints + (size_t)b * 7 * n : nullptr;
+    o.derived = g.derived ? g.derived + (size_t)b * 3 * (n - 1) : nullptr;
     return o;
 }
 
@@ -199,11 +203,12 @@ __global__ void __launch_bounds__(32, OCC) acmpc_speed_kernel(const __grid_const
     c.tm.a = 0;
     c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(c.W + acmpc::Layout<C>::kSpeedDoubles);
-    stage_path(c.W, p.paths + (size_t)b * 3 * H, H, p.use_tma, mbar, lane);
+    if (!p.way) stage_path(c.W, p.paths + (size_t)b * 3 * H, H, p.use_tma, mbar, lane);
     const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
     double* wrec = p.warm ? p.warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;
-    const int iters = acmpc::speed_instance<C>(c, c.W, vmax, p.is_localised, p.vel + (size_t)b * n,
-                                               slice_outputs(p.out, b, H), wrec, p.use_warm != 0);
+    const int iters = acmpc::speed_instance<C>(c, c.W, vmax, p.is_localised, p.vel ? p.vel + (size_t)b * n : nullptr,
+                                               slice_outputs(p.out, b, H), wrec, p.use_warm != 0,
+                                               p.way ? p.way + (size_t)b * 7 * n : nullptr);
     if (p.order && lane == 0) {   // class of this solve for the control kernel's queue: most iterations first
         const int per = p.cfg.check_termination > 0 ? p.cfg.check_termination : 25;
         int k = kOrderBins - iters / per;
@@ -294,17 +299,19 @@ struct acmpc_handle {
     size_t arena_bytes;
     void* h_stage;           // pinned mirror of the arena for small batches (one H2D + one D2H)
     size_t stage_bytes;
-    int32_t* d_order[4];     // longest-first order buffers (one per chunk stream), see KernelParams::order
-    size_t order_cap[4];     // instances each can hold
-    int order_parity[4];     // counter set of the last launch
+    // slots 0..3 = the host entry point's chunk streams, slot 4 (kDeviceSlot) = the device entry point, whose launches
+    // run on the caller's stream and must not share a ticket counter / order buffer with the handle's own streams
+    int32_t* d_order[5];     // longest-first order buffers, see KernelParams::order
+    size_t order_cap[5];     // instances each can hold
+    int order_parity[5];     // counter set of the last launch
     int order_on;            // ACMPC_ORDER=0 switches the ordering off
     int order_min;           // smallest batch that is ordered (ACMPC_ORDER_MIN, default 1024)
     void* d_warm;            // warm-start records of the host entry point (keep_warm)
     int warm_B;
     void* d_vel;             // speed-profile hand-over buffer of the device entry point (when v_ref is not requested)
     size_t vel_bytes;
-    uint32_t* d_queue;       // 4 ticket counters of the persistent warps (see KernelParams), one per chunk stream
-    uint32_t queue_pos[4];   // their values once every launch issued so far has completed
+    uint32_t* d_queue;       // 5 ticket counters of the persistent warps (see KernelParams), one per slot
+    uint32_t queue_pos[5];   // their values once every launch issued so far has completed
     int profiling;           // record events around the two kernels (acmpc_set_profiling)
     cudaEvent_t* ev;         // 3 * kEventRing events
     int ev_head, ev_count;
@@ -450,12 +457,11 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     p.persistent = h->persistent;
     if (p.persistent && ctas > resident) ctas = resident;
     p.queue = h->d_queue + qi, p.queue_base = h->queue_pos[qi], p.warps_launched = (uint32_t)(ctas * kWarpsPerCta);
-    if (p.persistent) h->queue_pos[qi] += (uint32_t)B;   // every solved instance draws one ticket
     // longest-first order for batches that run several rounds of the device (see KernelParams::order)
     p.order = nullptr;
     if (h->order_on && B >= h->order_min && h->d_order[qi] && (size_t)B <= h->order_cap[qi]) {
         p.order = h->d_order[qi];
-        p.order_set = (h->order_parity[qi] ^= 1);
+        p.order_set = h->order_parity[qi] ^ 1;
         if (d_vmax) {
             acmpc_order_kernel<<<(B + 255) / 256, 256, 0, stream>>>(d_vmax, B, h->cfg.v_min, h->cfg.v_max,
                                                                     p.order + 8 * p.order_set, p.order + 16);
@@ -474,12 +480,131 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
              "speed kernel launch"))
         return ACMPC_ERR_CUDA;
     if (ev) cudaEventRecord(ev[1], stream);
-    if (fail(h, cudaLaunchKernel(kernel_for(H), dim3(ctas), dim3(32 * kWarpsPerCta), args, smem, stream), "kernel launch"))
+    if (fail(h, cudaLaunchKernel(kernel_for(H), dim3(ctas), dim3(32 * kWarpsPerCta), args, smem, stream), "kernel launch")) {
+        h->order_cap[qi] = 0;   // the speed kernel has filled a counter set nobody will reset: rebuild the buffer
         return ACMPC_ERR_CUDA;
+    }
     if (ev) cudaEventRecord(ev[2], stream);
+    // host-side mirrors of the device counters move only once both kernels are in the stream: a failed launch leaves
+    // the ticket base and the counter-set parity where the device still has them
+    if (p.persistent) h->queue_pos[qi] += (uint32_t)B;   // every solved instance draws one ticket
+    if (p.order) h->order_parity[qi] = p.order_set;
     h->last_launches += 2, h->last_smem = (int)smem, h->last_threads = 32 * kWarpsPerCta, h->last_ipc = kWarpsPerCta;
     if (fail(h, cudaGetLastError(), "kernel launch")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
+}
+
+// small staged call: copy the inputs in, run `launch`, copy the outputs back, synchronise
+struct Staged {
+    acmpc_handle* h;
+    char* base = nullptr;
+    size_t used = 0, cap = 0;
+    int32_t rc = ACMPC_OK;
+    Staged(acmpc_handle* hh, size_t bytes) : h(hh), cap(bytes + 4096)
+    {
+        if (fail(h, cudaSetDevice(h->device), "cudaSetDevice") || fail(h, cudaMalloc((void**)&base, cap), "cudaMalloc(staged)"))
+            rc = ACMPC_ERR_CUDA;
+    }
+    ~Staged()
+    {
+        if (base) cudaFree(base);
+    }
+    void* in(const void* src, size_t bytes)
+    {
+        if (rc != ACMPC_OK || !src) return nullptr;
+        void* d = base + used;
+        used += (bytes + 255) & ~(size_t)255;
+        if (fail(h, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->stream), "H2D(staged)")) rc = ACMPC_ERR_CUDA;
+        return d;
+    }
+    void* out(const void* dst, size_t bytes)
+    {
+        if (rc != ACMPC_OK || !dst) return nullptr;
+        void* d = base + used;
+        used += (bytes + 255) & ~(size_t)255;
+        return d;
+    }
+    void* scratch(size_t bytes)
+    {
+        if (rc != ACMPC_OK) return nullptr;
+        void* d = base + used;
+        used += (bytes + 255) & ~(size_t)255;
+        return d;
+    }
+    void back(void* dst, const void* d, size_t bytes)
+    {
+        if (rc != ACMPC_OK || !dst) return;
+        if (fail(h, cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, h->stream), "D2H(staged)")) rc = ACMPC_ERR_CUDA;
+    }
+    int32_t finish(int launches, int threads)
+    {
+        if (rc == ACMPC_OK && (fail(h, cudaGetLastError(), "publish kernels") || fail(h, cudaStreamSynchronize(h->stream), "publish kernels")))
+            rc = ACMPC_ERR_CUDA;
+        if (rc == ACMPC_OK) h->last_launches = launches, h->last_smem = 0, h->last_threads = threads, h->last_ipc = 1;
+        return rc;
+    }
+};
+
+// The speed-profile kernel alone, on ReferencePath rows the caller built (SpatialMPC.compute_speed_profile).
+int launch_speed_only(acmpc_handle* h, int B, double* d_way, const double* d_vmax, int is_localised, int has_end_vel,
+                      double end_vel, double* d_solution, int32_t* d_status, int32_t* d_iters2, int32_t* d_rho2,
+                      double* d_warm, int use_warm, cudaStream_t stream)
+{
+    KernelParams p;
+    memset(&p, 0, sizeof(p));
+    p.cfg = h->cfg;
+    p.cfg.has_end_velocity = has_end_vel ? 1 : 0, p.cfg.end_velocity = has_end_vel ? end_vel : 0.0;
+    p.way = d_way, p.vmax = d_vmax, p.vel = d_solution;
+    p.out.status_speed = d_status, p.out.iters = d_iters2, p.out.rho_updates = d_rho2;
+    p.warm = d_warm, p.use_warm = (d_warm && use_warm) ? 1 : 0;
+    p.B = B, p.is_localised = is_localised ? 1 : 0;
+    const int H = h->cfg.horizon;
+    void* args[] = {&p};
+    const bool dense = B > 12 * h->sm_count;
+    if (fail(h, cudaLaunchKernel(speed_kernel_for(H, dense), dim3(B), dim3(32), args, speed_smem_bytes_for(H), stream),
+             "speed kernel launch") ||
+        fail(h, cudaGetLastError(), "speed kernel launch"))
+        return ACMPC_ERR_CUDA;
+    h->last_launches = 1, h->last_smem = (int)speed_smem_bytes_for(H), h->last_threads = 32, h->last_ipc = 1;
+    return ACMPC_OK;
+}
+
+// acmpc_outputs is 14 pointers in ABI order; per-instance element count and element size of field f
+constexpr int kNumFields = 14;
+static_assert(sizeof(acmpc_outputs) == kNumFields * sizeof(void*), "acmpc_outputs: one pointer per field");
+size_t field_elems(int f, int H)
+{
+    const size_t n = (size_t)H - 1;
+    switch (f) {
+        case 0: case 1: return 2 * n;           // controls, prediction
+        case 2: case 4: return n;               // cum_time, v_ref
+        case 3: return 3 * (size_t)H;           // states
+        case 5: case 6: case 7: return 1;       // cost, pri_res, dua_res
+        case 8: case 9: return 1;               // status, status_speed
+        case 10: case 11: return 2;             // iters, rho_updates
+        case 12: return 7 * n;                  // waypoints
+        default: return 3 * (n - 1);            // derived
+    }
+}
+size_t field_esize(int f) { return (f >= 8 && f <= 11) ? 4 : 8; }
+void* const& field_ptr(const acmpc_outputs& o, int f) { return reinterpret_cast<void* const*>(&o)[f]; }
+void*& field_ptr(acmpc_outputs& o, int f) { return reinterpret_cast<void**>(&o)[f]; }
+constexpr int kFieldVref = 4;
+
+// (re)allocate the host entry points' warm-start records: dropped when keep_warm is 0 or the batch size changes
+bool ensure_warm(acmpc_handle* h, int B, int keep_warm)
+{
+    if (!keep_warm || B != h->warm_B) {
+        if (h->d_warm) cudaFree(h->d_warm);
+        h->d_warm = nullptr, h->warm_B = 0;
+    }
+    if (keep_warm && !h->d_warm) {
+        const size_t wb = (size_t)B * warm_bytes_for(h->cfg.horizon);
+        if (fail(h, cudaMalloc(&h->d_warm, wb), "cudaMalloc(warm)")) return false;
+        if (fail(h, cudaMemsetAsync(h->d_warm, 0, wb, h->stream), "cudaMemset(warm)")) return false;
+        h->warm_B = B;
+    }
+    return true;
 }
 
 }  // namespace
@@ -503,6 +628,7 @@ void acmpc_default_config(acmpc_config* c)
     c->eps_abs = 1e-3, c->eps_rel = 1e-3, c->eps_prim_inf = 1e-4, c->eps_dual_inf = 1e-4;
     c->adaptive_rho_tolerance = 5.0;
     c->scaling = 10, c->check_termination = 25, c->adaptive_rho = 1, c->adaptive_rho_interval = 50;
+    c->check_dualgap = 0;   // OSQP 0.6.x termination test
 }
 
 int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out)
@@ -535,10 +661,11 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
     }
     h->sm_count = prop.multiProcessorCount;
     h->d_queue = nullptr;
-    for (int k = 0; k < 4; ++k) h->queue_pos[k] = 0, h->streams[k] = nullptr;
+    for (int k = 0; k < 4; ++k) h->streams[k] = nullptr;
+    for (int k = 0; k < kSlots; ++k) h->queue_pos[k] = 0;
     h->d_vel = nullptr, h->vel_bytes = 0;
     h->d_warm = nullptr, h->warm_B = 0;
-    for (int k = 0; k < 4; ++k) h->d_order[k] = nullptr, h->order_cap[k] = 0, h->order_parity[k] = 0;
+    for (int k = 0; k < kSlots; ++k) h->d_order[k] = nullptr, h->order_cap[k] = 0, h->order_parity[k] = 0;
     {
         const char* e = getenv("ACMPC_ORDER");
         h->order_on = (e && e[0] == '0') ? 0 : 1;
@@ -564,8 +691,8 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
         fail(h, cudaFuncSetAttribute(kernel_for(cfg->horizon), cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared),
              "cudaFuncSetAttribute(carveout)") ||
-        fail(h, cudaMalloc(&h->d_queue, 4 * sizeof(uint32_t)), "cudaMalloc(queue)") ||
-        fail(h, cudaMemset(h->d_queue, 0, 4 * sizeof(uint32_t)), "cudaMemset(queue)") ||
+        fail(h, cudaMalloc(&h->d_queue, kSlots * sizeof(uint32_t)), "cudaMalloc(queue)") ||
+        fail(h, cudaMemset(h->d_queue, 0, kSlots * sizeof(uint32_t)), "cudaMemset(queue)") ||
         fail(h, cudaStreamCreateWithFlags(&h->streams[0], cudaStreamNonBlocking), "cudaStreamCreate") ||
         fail(h, cudaStreamCreateWithFlags(&h->streams[1], cudaStreamNonBlocking), "cudaStreamCreate") ||
         fail(h, cudaStreamCreateWithFlags(&h->streams[2], cudaStreamNonBlocking), "cudaStreamCreate") ||
@@ -607,7 +734,7 @@ int32_t acmpc_destroy(acmpc_handle* h)
     if (h->d_queue) cudaFree(h->d_queue);
     if (h->d_vel) cudaFree(h->d_vel);
     if (h->d_warm) cudaFree(h->d_warm);
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < kSlots; ++k)
         if (h->d_order[k]) cudaFree(h->d_order[k]);
     if (h->ev) {
         for (int i = 0; i < 3 * kEventRing; ++i) cudaEventDestroy(h->ev[i]);
@@ -643,7 +770,7 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
     if (B == 0) return ACMPC_OK;
     if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
     h->last_launches = 0;
-    if (!ensure_order(h, 0, B)) return ACMPC_ERR_CUDA;
+    if (!ensure_order(h, kDeviceSlot, B)) return ACMPC_ERR_CUDA;
     double* d_vel = d_out->v_ref;
     if (!d_vel) {   // the caller did not ask for v_ref: hand over through a scratch buffer owned by the handle
         const size_t need = (size_t)B * (h->cfg.horizon - 1) * sizeof(double);
@@ -653,23 +780,13 @@ int32_t acmpc_solve_batch_device(acmpc_handle* h, int32_t B, const double* d_pat
                 cudaFree(h->d_vel);
             }
             h->d_vel = nullptr, h->vel_bytes = 0;
-    h->d_warm = nullptr, h->warm_B = 0;
-    for (int k = 0; k < 4; ++k) h->d_order[k] = nullptr, h->order_cap[k] = 0, h->order_parity[k] = 0;
-    {
-        const char* e = getenv("ACMPC_ORDER");
-        h->order_on = (e && e[0] == '0') ? 0 : 1;
-        const char* m = getenv("ACMPC_ORDER_MIN");
-        h->order_min = m ? atoi(m) : 1024;
-        if (h->order_min < 1) h->order_min = 1;
-    }
-    h->profiling = 0, h->ev = nullptr, h->ev_head = 0, h->ev_count = 0;
             if (fail(h, cudaMalloc(&h->d_vel, need), "cudaMalloc(vel)")) return ACMPC_ERR_CUDA;
             h->vel_bytes = need;
         }
         d_vel = static_cast<double*>(h->d_vel);
     }
     return launch(h, B, d_paths, d_offsets, d_vmax, is_localised, d_out, d_vel, static_cast<double*>(d_warm),
-                  warm_valid, static_cast<cudaStream_t>(stream));
+                  warm_valid, static_cast<cudaStream_t>(stream), kDeviceSlot);
 }
 
 int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, const double* offsets,
@@ -685,39 +802,37 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
     if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
     // keep_warm: the handle plays the reference's persistent solver objects -- one zero-initialised record
     // per instance slot, dropped (cold restart) when the batch size changes or keep_warm is 0
-    if (!keep_warm || B != h->warm_B) {
-        if (h->d_warm) cudaFree(h->d_warm);
-        h->d_warm = nullptr, h->warm_B = 0;
-    }
-    if (keep_warm && !h->d_warm) {
-        const size_t wb = (size_t)B * warm_bytes_for(h->cfg.horizon);
-        if (fail(h, cudaMalloc(&h->d_warm, wb), "cudaMalloc(warm)")) return ACMPC_ERR_CUDA;
-        if (fail(h, cudaMemsetAsync(h->d_warm, 0, wb, h->stream), "cudaMemset(warm)")) return ACMPC_ERR_CUDA;
-        h->warm_B = B;
-    }
-    const int H = h->cfg.horizon, n = H - 1;
+    if (!ensure_warm(h, B, keep_warm)) return ACMPC_ERR_CUDA;
+    const int H = h->cfg.horizon;
     const size_t nb = (size_t)B;
-    // arena layout (all 16-byte aligned): inputs then one slab per output field
+    // arena layout (all 256-byte aligned): inputs then one slab per output field
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align(off + bytes); return o; };
     const size_t o_paths = take(nb * 3 * H * 8), o_off = take(nb * 8), o_vmax = take(nb * 8);
-    const size_t o_ctrl = take(nb * 2 * n * 8), o_pred = take(nb * 2 * n * 8), o_ct = take(nb * n * 8);
-    const size_t o_st = take(nb * 3 * H * 8), o_vr = take(nb * n * 8), o_cost = take(nb * 8);
-    const size_t o_pr = take(nb * 8), o_dr = take(nb * 8), o_stat = take(nb * 4), o_ss = take(nb * 4);
-    const size_t o_it = take(nb * 8), o_ru = take(nb * 8), o_wp = take(nb * 7 * n * 8);
+    size_t o_f[kNumFields], per_b[kNumFields];
+    for (int f = 0; f < kNumFields; ++f) per_b[f] = field_elems(f, H) * field_esize(f), o_f[f] = take(nb * per_b[f]);
     if (off > h->arena_bytes) {
+        for (int k = 0; k < 4; ++k)   // an earlier call's copies are done (every call ends with a sync); be explicit
+            if (fail(h, cudaStreamSynchronize(h->streams[k]), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
         if (h->d_arena) cudaFree(h->d_arena);
         h->d_arena = nullptr, h->arena_bytes = 0;
-    h->h_stage = nullptr, h->stage_bytes = 0;
         if (fail(h, cudaMalloc(&h->d_arena, off), "cudaMalloc(arena)")) return ACMPC_ERR_CUDA;
         h->arena_bytes = off;
     }
     char* base = static_cast<char*>(h->d_arena);
     const size_t wstride = warm_bytes_for(H);
     h->last_launches = 0;
+    // device-side output struct of the instances [z, z + ...): requested fields only (v_ref is always the hand-over)
+    auto device_outputs = [&](size_t z) {
+        acmpc_outputs d;
+        memset(&d, 0, sizeof(d));
+        for (int f = 0; f < kNumFields; ++f)
+            if (field_ptr(*out, f)) field_ptr(d, f) = base + o_f[f] + z * per_b[f];
+        return d;
+    };
     // Small batches (the B = 1 drop-in call): inputs and outputs go through ONE pinned staging buffer that mirrors
-    // the arena -- one H2D, the kernels, one D2H, then plain memcpys -- instead of 3 + 13 separate copies.
+    // the arena -- one H2D, the kernels, one D2H, then plain memcpys -- instead of 3 + 14 separate copies.
     if (B <= 64) {
         if (off > h->stage_bytes) {
             if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -730,48 +845,24 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
         memcpy(st + o_paths, paths, nb * 3 * H * 8);
         if (offsets) memcpy(st + o_off, offsets, nb * 8);
         if (vmax) memcpy(st + o_vmax, vmax, nb * 8);
-        if (fail(h, cudaMemcpyAsync(base, st, o_ctrl, cudaMemcpyHostToDevice, s), "H2D inputs")) return ACMPC_ERR_CUDA;
-        acmpc_outputs d;
-        memset(&d, 0, sizeof(d));
-        if (out->controls) d.controls = reinterpret_cast<double*>(base + o_ctrl);
-        if (out->prediction) d.prediction = reinterpret_cast<double*>(base + o_pred);
-        if (out->cum_time) d.cum_time = reinterpret_cast<double*>(base + o_ct);
-        if (out->states) d.states = reinterpret_cast<double*>(base + o_st);
-        if (out->v_ref) d.v_ref = reinterpret_cast<double*>(base + o_vr);
-        if (out->cost) d.cost = reinterpret_cast<double*>(base + o_cost);
-        if (out->pri_res) d.pri_res = reinterpret_cast<double*>(base + o_pr);
-        if (out->dua_res) d.dua_res = reinterpret_cast<double*>(base + o_dr);
-        if (out->status) d.status = reinterpret_cast<int32_t*>(base + o_stat);
-        if (out->status_speed) d.status_speed = reinterpret_cast<int32_t*>(base + o_ss);
-        if (out->iters) d.iters = reinterpret_cast<int32_t*>(base + o_it);
-        if (out->rho_updates) d.rho_updates = reinterpret_cast<int32_t*>(base + o_ru);
-        if (out->waypoints) d.waypoints = reinterpret_cast<double*>(base + o_wp);
+        if (fail(h, cudaMemcpyAsync(base, st, o_f[0], cudaMemcpyHostToDevice, s), "H2D inputs")) return ACMPC_ERR_CUDA;
+        const acmpc_outputs d = device_outputs(0);
         int rc = launch(h, B, reinterpret_cast<const double*>(base + o_paths),
                         offsets ? reinterpret_cast<const double*>(base + o_off) : nullptr,
                         vmax ? reinterpret_cast<const double*>(base + o_vmax) : nullptr, is_localised, &d,
-                        reinterpret_cast<double*>(base + o_vr), static_cast<double*>(h->d_warm), 1, s, 0);
+                        reinterpret_cast<double*>(base + o_f[kFieldVref]), static_cast<double*>(h->d_warm), 1, s, 0);
         if (rc != ACMPC_OK) return rc;
         // the requested fields form a sub-range of the arena's output region: copy from its first to its last byte
-        const size_t o_end = out->waypoints ? off : o_wp;
-        if (fail(h, cudaMemcpyAsync(st + o_ctrl, base + o_ctrl, o_end - o_ctrl, cudaMemcpyDeviceToHost, s), "D2H outputs") ||
-            fail(h, cudaStreamSynchronize(s), "cudaStreamSynchronize"))
-            return ACMPC_ERR_CUDA;
-#define ACMPC_UNSTAGE(field, o, bytes) \
-    if (out->field) memcpy(out->field, st + (o), (bytes));
-        ACMPC_UNSTAGE(controls, o_ctrl, nb * 2 * n * 8)
-        ACMPC_UNSTAGE(prediction, o_pred, nb * 2 * n * 8)
-        ACMPC_UNSTAGE(cum_time, o_ct, nb * n * 8)
-        ACMPC_UNSTAGE(states, o_st, nb * 3 * H * 8)
-        ACMPC_UNSTAGE(v_ref, o_vr, nb * n * 8)
-        ACMPC_UNSTAGE(cost, o_cost, nb * 8)
-        ACMPC_UNSTAGE(pri_res, o_pr, nb * 8)
-        ACMPC_UNSTAGE(dua_res, o_dr, nb * 8)
-        ACMPC_UNSTAGE(status, o_stat, nb * 4)
-        ACMPC_UNSTAGE(status_speed, o_ss, nb * 4)
-        ACMPC_UNSTAGE(iters, o_it, nb * 8)
-        ACMPC_UNSTAGE(rho_updates, o_ru, nb * 8)
-        ACMPC_UNSTAGE(waypoints, o_wp, nb * 7 * n * 8)
-#undef ACMPC_UNSTAGE
+        int f_lo = kNumFields, f_hi = -1;
+        for (int f = 0; f < kNumFields; ++f)
+            if (field_ptr(*out, f)) f_lo = f < f_lo ? f : f_lo, f_hi = f;
+        if (f_hi >= 0) {
+            const size_t lo = o_f[f_lo], hi = o_f[f_hi] + nb * per_b[f_hi];
+            if (fail(h, cudaMemcpyAsync(st + lo, base + lo, hi - lo, cudaMemcpyDeviceToHost, s), "D2H outputs")) return ACMPC_ERR_CUDA;
+        }
+        if (fail(h, cudaStreamSynchronize(s), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
+        for (int f = 0; f < kNumFields; ++f)
+            if (field_ptr(*out, f)) memcpy(field_ptr(*out, f), st + o_f[f], nb * per_b[f]);
         return ACMPC_OK;
     }
     // Large batches go through as up to 4 chunks on 4 streams (own ticket queue each), so that the H2D copy of
@@ -808,49 +899,83 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
         if (vmax && fail(h, cudaMemcpyAsync(base + o_vmax + z * 8, vmax + z, nbk * 8, cudaMemcpyHostToDevice, s),
                          "H2D vmax"))
             return ACMPC_ERR_CUDA;
-        acmpc_outputs d;
-        memset(&d, 0, sizeof(d));
-        if (out->controls) d.controls = reinterpret_cast<double*>(base + o_ctrl) + z * 2 * n;
-        if (out->prediction) d.prediction = reinterpret_cast<double*>(base + o_pred) + z * 2 * n;
-        if (out->cum_time) d.cum_time = reinterpret_cast<double*>(base + o_ct) + z * n;
-        if (out->states) d.states = reinterpret_cast<double*>(base + o_st) + z * 3 * H;
-        if (out->v_ref) d.v_ref = reinterpret_cast<double*>(base + o_vr) + z * n;
-        if (out->cost) d.cost = reinterpret_cast<double*>(base + o_cost) + z;
-        if (out->pri_res) d.pri_res = reinterpret_cast<double*>(base + o_pr) + z;
-        if (out->dua_res) d.dua_res = reinterpret_cast<double*>(base + o_dr) + z;
-        if (out->status) d.status = reinterpret_cast<int32_t*>(base + o_stat) + z;
-        if (out->status_speed) d.status_speed = reinterpret_cast<int32_t*>(base + o_ss) + z;
-        if (out->iters) d.iters = reinterpret_cast<int32_t*>(base + o_it) + z * 2;
-        if (out->rho_updates) d.rho_updates = reinterpret_cast<int32_t*>(base + o_ru) + z * 2;
-        if (out->waypoints) d.waypoints = reinterpret_cast<double*>(base + o_wp) + z * 7 * n;
+        const acmpc_outputs d = device_outputs(z);
         int rc = launch(h, cb, reinterpret_cast<const double*>(base + o_paths) + z * 3 * H,
                         offsets ? reinterpret_cast<const double*>(base + o_off) + z : nullptr,
                         vmax ? reinterpret_cast<const double*>(base + o_vmax) + z : nullptr, is_localised, &d,
-                        reinterpret_cast<double*>(base + o_vr) + z * n,
+                        reinterpret_cast<double*>(base + o_f[kFieldVref]) + z * (H - 1),
                         h->d_warm ? reinterpret_cast<double*>(static_cast<char*>(h->d_warm) + z * wstride) : nullptr, 1, s, qi);
         if (rc != ACMPC_OK) return rc;
-#define ACMPC_D2H(field, per_inst, type)                                                                        \
-    if (out->field && fail(h, cudaMemcpyAsync(out->field + z * (per_inst), d.field, nbk * (per_inst) * sizeof(type), \
-                                              cudaMemcpyDeviceToHost, s), "D2H " #field))                        \
-        return ACMPC_ERR_CUDA;
-        ACMPC_D2H(controls, 2 * n, double)
-        ACMPC_D2H(prediction, 2 * n, double)
-        ACMPC_D2H(cum_time, n, double)
-        ACMPC_D2H(states, 3 * H, double)
-        ACMPC_D2H(v_ref, n, double)
-        ACMPC_D2H(cost, 1, double)
-        ACMPC_D2H(pri_res, 1, double)
-        ACMPC_D2H(dua_res, 1, double)
-        ACMPC_D2H(status, 1, int32_t)
-        ACMPC_D2H(status_speed, 1, int32_t)
-        ACMPC_D2H(iters, 2, int32_t)
-        ACMPC_D2H(rho_updates, 2, int32_t)
-        ACMPC_D2H(waypoints, 7 * n, double)
-#undef ACMPC_D2H
+        for (int f = 0; f < kNumFields; ++f)
+            if (field_ptr(*out, f) &&
+                fail(h, cudaMemcpyAsync(static_cast<char*>(field_ptr(*out, f)) + z * per_b[f], field_ptr(d, f), nbk * per_b[f],
+                                        cudaMemcpyDeviceToHost, s), "D2H outputs"))
+                return ACMPC_ERR_CUDA;
     }
     for (int k = 0; k < 4; ++k)
         if (fail(h, cudaStreamSynchronize(h->streams[k]), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
     return ACMPC_OK;
+}
+
+int32_t acmpc_speed_profile_batch_device(acmpc_handle* h, int32_t B, double* d_waypoints, const double* d_vmax,
+                                         int32_t is_localised, int32_t has_end_vel, double end_vel, void* d_warm,
+                                         int32_t warm_valid, double* d_solution, int32_t* d_status, int32_t* d_iters,
+                                         int32_t* d_rho_updates, void* stream)
+{
+    if (!h) return ACMPC_ERR_INVALID;
+    if (B < 0 || (B > 0 && !d_waypoints) || (warm_valid && !d_warm) || (d_warm && (reinterpret_cast<uintptr_t>(d_warm) & 7))) {
+        h->err = "bad arguments";
+        return ACMPC_ERR_INVALID;
+    }
+    if (B == 0) return ACMPC_OK;
+    if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    return launch_speed_only(h, B, d_waypoints, d_vmax, is_localised, has_end_vel, end_vel, d_solution, d_status, d_iters,
+                             d_rho_updates, static_cast<double*>(d_warm), warm_valid, static_cast<cudaStream_t>(stream));
+}
+
+int32_t acmpc_speed_profile_batch_host(acmpc_handle* h, int32_t B, double* waypoints, const double* vmax,
+                                       int32_t is_localised, int32_t has_end_vel, double end_vel, int32_t keep_warm,
+                                       double* solution, int32_t* status, int32_t* iters, int32_t* rho_updates)
+{
+    if (!h) return ACMPC_ERR_INVALID;
+    if (B < 0 || (B > 0 && !waypoints)) {
+        h->err = "bad arguments";
+        return ACMPC_ERR_INVALID;
+    }
+    if (B == 0) return ACMPC_OK;
+    if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    if (!ensure_warm(h, B, keep_warm)) return ACMPC_ERR_CUDA;
+    const int n = h->cfg.horizon - 1;
+    const size_t nb = (size_t)B, way_b = nb * 7 * n * 8;
+    Staged s(h, way_b + nb * (8 + (size_t)n * 8 + 4 + 8 + 8) + 8 * 256);
+    double* d_way = (double*)s.in(waypoints, way_b);
+    const double* d_vm = (const double*)s.in(vmax, nb * 8);
+    double* d_sol = (double*)s.scratch(nb * n * 8);
+    int32_t* d_st = (int32_t*)s.scratch(nb * 4);
+    int32_t* d_it = (int32_t*)s.scratch(nb * 8);      // the kernels write [B,2] (speed QP, control QP) pairs
+    int32_t* d_ru = (int32_t*)s.scratch(nb * 8);
+    if (s.rc == ACMPC_OK) {
+        const int32_t rc = launch_speed_only(h, B, d_way, d_vm, is_localised, has_end_vel, end_vel, d_sol, d_st, d_it, d_ru,
+                                             static_cast<double*>(h->d_warm), 1, h->stream);
+        if (rc != ACMPC_OK) return rc;
+    }
+    // only the velocities row can have changed
+    std::vector<int32_t> it2(iters || rho_updates ? 2 * nb : 0), ru2(rho_updates ? 2 * nb : 0);
+    if (s.rc == ACMPC_OK &&
+        fail(h, cudaMemcpy2DAsync(waypoints + 6 * (size_t)n, 7 * (size_t)n * 8, d_way + 6 * (size_t)n, 7 * (size_t)n * 8,
+                                  (size_t)n * 8, nb, cudaMemcpyDeviceToHost, h->stream), "D2H(velocities)"))
+        s.rc = ACMPC_ERR_CUDA;
+    s.back(solution, d_sol, nb * n * 8);
+    s.back(status, d_st, nb * 4);
+    if (iters) s.back(it2.data(), d_it, nb * 8);
+    if (rho_updates) s.back(ru2.data(), d_ru, nb * 8);
+    const int32_t rc = s.finish(1, 32);
+    if (rc == ACMPC_OK)
+        for (size_t b = 0; b < nb; ++b) {
+            if (iters) iters[b] = it2[2 * b];
+            if (rho_updates) rho_updates[b] = ru2[2 * b];
+        }
+    return rc;
 }
 
 int32_t acmpc_last_launch_info(const acmpc_handle* h, int32_t* n_launches, int32_t* smem_bytes,
@@ -1117,57 +1242,6 @@ int32_t acmpc_reference_speeds_host(acmpc_handle* h, int32_t n, const double* ve
 // ---- caller side of the step (publish.cuh) --------------------------------------------------------------------
 namespace {
 
-// small staged call: copy the inputs in, run `launch`, copy the outputs back, synchronise
-struct Staged {
-    acmpc_handle* h;
-    char* base = nullptr;
-    size_t used = 0, cap = 0;
-    int32_t rc = ACMPC_OK;
-    Staged(acmpc_handle* hh, size_t bytes) : h(hh), cap(bytes + 4096)
-    {
-        if (fail(h, cudaSetDevice(h->device), "cudaSetDevice") || fail(h, cudaMalloc((void**)&base, cap), "cudaMalloc(staged)"))
-            rc = ACMPC_ERR_CUDA;
-    }
-    ~Staged()
-    {
-        if (base) cudaFree(base);
-    }
-    void* in(const void* src, size_t bytes)
-    {
-        if (rc != ACMPC_OK || !src) return nullptr;
-        void* d = base + used;
-        used += (bytes + 255) & ~(size_t)255;
-        if (fail(h, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->stream), "H2D(staged)")) rc = ACMPC_ERR_CUDA;
-        return d;
-    }
-    void* out(const void* dst, size_t bytes)
-    {
-        if (rc != ACMPC_OK || !dst) return nullptr;
-        void* d = base + used;
-        used += (bytes + 255) & ~(size_t)255;
-        return d;
-    }
-    void* scratch(size_t bytes)
-    {
-        if (rc != ACMPC_OK) return nullptr;
-        void* d = base + used;
-        used += (bytes + 255) & ~(size_t)255;
-        return d;
-    }
-    void back(void* dst, const void* d, size_t bytes)
-    {
-        if (rc != ACMPC_OK || !dst) return;
-        if (fail(h, cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, h->stream), "D2H(staged)")) rc = ACMPC_ERR_CUDA;
-    }
-    int32_t finish(int launches, int threads)
-    {
-        if (rc == ACMPC_OK && (fail(h, cudaGetLastError(), "publish kernels") || fail(h, cudaStreamSynchronize(h->stream), "publish kernels")))
-            rc = ACMPC_ERR_CUDA;
-        if (rc == ACMPC_OK) h->last_launches = launches, h->last_smem = 0, h->last_threads = threads, h->last_ipc = 1;
-        return rc;
-    }
-};
-
 template <typename T>
 int32_t select_commands(acmpc_handle* h, int32_t B, int32_t n, const T* cum_time, const T* commands, const double* elapsed,
                         int32_t mode, T* out, int32_t* indices)
@@ -1247,27 +1321,79 @@ int32_t acmpc_select_commands_f64_host(acmpc_handle* h, int32_t B, int32_t n, co
 
 // ---- track side of the step: track_prep.cuh ---------------------------------------
 
-int32_t acmpc_remove_near_duplicates_host(acmpc_handle* h, int32_t M, const double* xy, double tol, double* out, int32_t* kept)
+int32_t acmpc_remove_near_duplicates_cols_host(acmpc_handle* h, int32_t M, int32_t cols, const double* rows, double tol,
+                                               double* out, int32_t* kept)
 {
-    if (!h || M < 0 || !kept || (M > 0 && (!xy || !out))) return ACMPC_ERR_INVALID;
+    if (!h || M < 0 || cols < 2 || !kept || (M > 0 && (!rows || !out))) return ACMPC_ERR_INVALID;
     if (M == 0) {
         *kept = 0;
         return ACMPC_OK;
     }
     const int ctas = (M + acmpc::trk::kDupThreads - 1) / acmpc::trk::kDupThreads;
-    const size_t b = (size_t)M * 2 * 8;
+    const size_t b = (size_t)M * cols * 8;
     Staged s(h, 2 * b + (size_t)ctas * 4 + 4 * 256);
-    const double* d_in = (const double*)s.in(xy, b);
+    const double* d_in = (const double*)s.in(rows, b);
     double* d_out = (double*)s.out(out, b);
     int* d_cnt = (int*)s.scratch((size_t)ctas * 4);
     int* d_kept = (int*)s.scratch(4);
     if (s.rc == ACMPC_OK) {
-        acmpc::trk::near_duplicate_count_kernel<<<ctas, acmpc::trk::kDupThreads, 0, h->stream>>>(d_in, M, tol, d_cnt);
-        acmpc::trk::near_duplicate_scatter_kernel<<<ctas, acmpc::trk::kDupThreads, 0, h->stream>>>(d_in, M, tol, d_cnt, d_out, d_kept);
+        acmpc::trk::near_duplicate_count_kernel<<<ctas, acmpc::trk::kDupThreads, 0, h->stream>>>(d_in, M, cols, tol, d_cnt);
+        acmpc::trk::near_duplicate_scatter_kernel<<<ctas, acmpc::trk::kDupThreads, 0, h->stream>>>(d_in, M, cols, tol, d_cnt, d_out, d_kept);
     }
     s.back(kept, d_kept, 4);
     s.back(out, d_out, b);     // rows [kept, M) of `out` are unspecified
     return s.finish(2, acmpc::trk::kDupThreads);
+}
+
+int32_t acmpc_remove_near_duplicates_host(acmpc_handle* h, int32_t M, const double* xy, double tol, double* out, int32_t* kept)
+{
+    return acmpc_remove_near_duplicates_cols_host(h, M, 2, xy, tol, out, kept);
+}
+
+// ---- SpatialBicycleModel / update_prediction as stand-alone entry points (model.cuh) ------------------------------------
+int32_t acmpc_t2s_host(acmpc_handle* h, int32_t B, const double* waypoints, const double* states, double* out)
+{
+    if (!h || B < 1 || !waypoints || !states || !out) return ACMPC_ERR_INVALID;
+    const size_t b = (size_t)B * 3 * 8;
+    Staged s(h, 3 * b + 4 * 256);
+    const double* d_w = (const double*)s.in(waypoints, b);
+    const double* d_s = (const double*)s.in(states, b);
+    double* d_o = (double*)s.out(out, b);
+    if (s.rc == ACMPC_OK) acmpc::model::t2s_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(d_w, d_s, B, d_o);
+    s.back(out, d_o, b);
+    return s.finish(1, 128);
+}
+
+int32_t acmpc_s2t_host(acmpc_handle* h, int32_t B, int32_t n, const double* waypoints, const double* states, double* out,
+                       double* prediction)
+{
+    if (!h || B < 1 || n < 1 || !waypoints || !states || (!out && !prediction)) return ACMPC_ERR_INVALID;
+    const size_t e = (size_t)B * n;
+    Staged s(h, e * (7 + 3 + 3 + 2) * 8 + 6 * 256);
+    const double* d_w = (const double*)s.in(waypoints, e * 7 * 8);
+    const double* d_s = (const double*)s.in(states, e * 3 * 8);
+    double* d_o = (double*)s.out(out, e * 3 * 8);
+    double* d_p = (double*)s.out(prediction, e * 2 * 8);
+    if (s.rc == ACMPC_OK) acmpc::model::s2t_kernel<<<(unsigned)((e + 127) / 128), 128, 0, h->stream>>>(d_w, d_s, B, n, d_o, d_p);
+    s.back(out, d_o, e * 3 * 8);
+    s.back(prediction, d_p, e * 2 * 8);
+    return s.finish(1, 128);
+}
+
+int32_t acmpc_linearise_host(acmpc_handle* h, int32_t B, int32_t n, const double* waypoints, double* f, double* A, double* Bm)
+{
+    if (!h || B < 1 || n < 1 || !waypoints || (!f && !A && !Bm)) return ACMPC_ERR_INVALID;
+    const size_t e = (size_t)B * n;
+    Staged s(h, e * (7 + 3 + 9 + 6) * 8 + 6 * 256);
+    const double* d_w = (const double*)s.in(waypoints, e * 7 * 8);
+    double* d_f = (double*)s.out(f, e * 3 * 8);
+    double* d_a = (double*)s.out(A, e * 9 * 8);
+    double* d_b = (double*)s.out(Bm, e * 6 * 8);
+    if (s.rc == ACMPC_OK) acmpc::model::linearise_kernel<<<(unsigned)((e + 127) / 128), 128, 0, h->stream>>>(d_w, B, n, d_f, d_a, d_b);
+    s.back(f, d_f, e * 3 * 8);
+    s.back(A, d_a, e * 9 * 8);
+    s.back(Bm, d_b, e * 6 * 8);
+    return s.finish(1, 128);
 }
 
 static int32_t polyfit_tracks(acmpc_handle* h, int32_t B, const int32_t* offsets, const double* points, const double* points_b,

@@ -173,6 +173,7 @@ struct RhoSet {
 struct Norms {
     double pri, dua, nz, nAx, nq, nAty, nPx;               // unscaled (termination)
     double s_pri, s_dua, s_z, s_Ax, s_q, s_Aty, s_Px;      // scaled (rho estimate)
+    double xtPx, qtx, sc;                                  // scaled x'Px, q'x, SC(y): OSQP 1.x duality-gap test only
 };
 
 struct SolveInfo {
@@ -232,6 +233,18 @@ AC_DEV VD project_dy(const VD& dy, const VD& lo, const VD& hi)
 AC_DEV VD support(const VD& dy, const VD& lo, const VD& hi)
 {
     return hi * vmax(dy, VD(0.0)) + lo * vmin(dy, VD(0.0));
+}
+// SC(y) of OSQP 1.x's duality gap: the same support function over the FINITE bounds only
+AC_DEV VD support_finite(const VD& y, const VD& lo, const VD& hi)
+{
+    return vsel(hi < VD(kBig), hi * vmax(y, VD(0.0)), VD(0.0)) + vsel(lo > VD(-kBig), lo * vmin(y, VD(0.0)), VD(0.0));
+}
+// OSQP 1.x check_dualgap: |x'Px + q'x + SC(y)| < eps_abs + eps_rel max(|x'Px|, |q'x|, |SC(y)|), all unscaled by 1/c
+AC_DEV bool dualgap_ok(const Norms& N, double cinv, double eps_abs, double eps_rel)
+{
+    const double gap = cinv * (N.xtPx + N.qtx + N.sc);
+    const double rel = cinv * fmax(fabs(N.xtPx), fmax(fabs(N.qtx), fabs(N.sc)));
+    return fabs(gap) < eps_abs + eps_rel * rel;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -602,6 +615,16 @@ struct SpeedQP {
             acc_col(v, q[j], p[j] * x[j], aty, di[j]);
         }
         finish_norms(v, cinv, nq_unscaled, nq_scaled, N);
+        if (c.cfg->check_dualgap) {
+            VD a = VD(0.0), b = VD(0.0), s = VD(0.0);
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                a = a + p[j] * x[j] * x[j];
+                b = b + q[j] * x[j];
+                s = s + support_finite(ya[j], la[j], ua[j]) + support_finite(yb[j], lb[j], ub[j]);
+            }
+            N.xtPx = wsum(a), N.qtx = wsum(b), N.sc = wsum(s);
+        }
     }
 
     AC_MEM int primal_infeasible(double eps)
@@ -662,7 +685,8 @@ struct SpeedQP {
         int p_inf = 0, d_inf = 0;
         if (!p_ok) p_inf = primal_infeasible(k * g.eps_prim_inf);
         if (!d_ok) d_inf = dual_infeasible(k * g.eps_dual_inf);
-        if (p_ok && d_ok) return approximate ? ACMPC_SOLVED_INACCURATE : ACMPC_SOLVED;
+        const int g_ok = g.check_dualgap ? uni(dualgap_ok(N, cinv, k * g.eps_abs, k * g.eps_rel)) : 1;
+        if (p_ok && d_ok && g_ok) return approximate ? ACMPC_SOLVED_INACCURATE : ACMPC_SOLVED;
         if (p_inf) return approximate ? ACMPC_PRIMAL_INFEASIBLE_INACCURATE : ACMPC_PRIMAL_INFEASIBLE;
         if (d_inf) return approximate ? ACMPC_DUAL_INFEASIBLE_INACCURATE : ACMPC_DUAL_INFEASIBLE;
         return 0;
@@ -1371,6 +1395,21 @@ struct ControlQP {
             }
         }
         finish_norms(v, cinv, nq_unscaled, nq_scaled, N);
+        if (c.cfg->check_dualgap) {
+            VD a = VD(0.0), b = VD(0.0), s = VD(0.0);
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) {
+                VD Hc[16];
+                c.tld(T_H, j, Hc);
+                for (int r = 0; r < 3; ++r) s = s + Hc[HC_BE + r] * ye[j][r];   // l == u == b
+                for (int e = 0; e < 5; ++e) {
+                    a = a + c.ld(K_P + e, j) * x[j][e] * x[j][e];
+                    if (e >= 3) b = b + Hc[HC_Q + e - 3] * x[j][e];
+                    s = s + support_finite(yb[j][e], Hc[HC_LB + e], Hc[HC_UB + e]);
+                }
+            }
+            N.xtPx = wsum(a), N.qtx = wsum(b), N.sc = wsum(s);
+        }
     }
 
     AC_MEM int primal_infeasible(double eps)
@@ -1451,7 +1490,8 @@ struct ControlQP {
         int p_inf = 0, d_inf = 0;
         if (!p_ok) p_inf = primal_infeasible(k * g.eps_prim_inf);
         if (!d_ok) d_inf = dual_infeasible(k * g.eps_dual_inf);
-        if (p_ok && d_ok) return approximate ? ACMPC_SOLVED_INACCURATE : ACMPC_SOLVED;
+        const int g_ok = g.check_dualgap ? uni(dualgap_ok(N, cinv, k * g.eps_abs, k * g.eps_rel)) : 1;
+        if (p_ok && d_ok && g_ok) return approximate ? ACMPC_SOLVED_INACCURATE : ACMPC_SOLVED;
         if (p_inf) return approximate ? ACMPC_PRIMAL_INFEASIBLE_INACCURATE : ACMPC_PRIMAL_INFEASIBLE;
         if (d_inf) return approximate ? ACMPC_DUAL_INFEASIBLE_INACCURATE : ACMPC_DUAL_INFEASIBLE;
         return 0;
@@ -1569,18 +1609,34 @@ struct InstanceOut {
     double *controls, *prediction, *cum_time, *states, *v_ref, *cost, *pri_res, *dua_res;
     int32_t *status, *status_speed, *iters, *rho_updates;
     double* waypoints;
+    double* derived;
 };
 
 // Phase 1 of the step: waypoints + speed-profile QP (spatial_mpc.py:176-184).  Uses registers and the scratch
 // region only.  `vel_out` [n] always receives the profile (zeros unless the QP status is "solved",
 // spatial_mpc.py:115-122); it is the hand-over to phase 2.
+// `way` != nullptr: the stand-alone SpatialMPC.compute_speed_profile (spatial_mpc.py:89-123) on a ReferencePath the
+// caller built -- kappas / distances are read from rows 3 / 4 of way[7,n] instead of a raw path, the velocities row
+// is written only when the QP is "solved" (left untouched otherwise) and vel_out (may be NULL) receives dec.x as is.
 template <int C>
 AC_DEV int speed_instance(const Ctx<C>& c, const double* raw_path, double v_max_live, int localised,
-                          double* vel_out, const InstanceOut& o, double* warm = nullptr, bool use_warm = false)
+                          double* vel_out, const InstanceOut& o, double* warm = nullptr, bool use_warm = false,
+                          double* way = nullptr)
 {
     const int n = c.n;
     PathRegs<C> path;
-    build_waypoints<C>(c, raw_path, path);
+    if (way) {
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VI st = c.stage(j);
+            VB ok = vi_lt(st, n);
+            path.xs[j] = path.ys[j] = path.psi[j] = path.wid[j] = VD(0.0);
+            path.kap[j] = ld_idx_if(ok, way + 3 * n, st, 0.0);
+            path.dist[j] = ld_idx_if(ok, way + 4 * n, st, 0.0);
+        }
+    } else {
+        build_waypoints<C>(c, raw_path, path);
+    }
     warp_sync();
     SolveInfo si;
     VD vel[C];
@@ -1591,6 +1647,11 @@ AC_DEV int speed_instance(const Ctx<C>& c, const double* raw_path, double v_max_
     for (int j = 0; j < C; ++j) {
         VI st = c.stage(j);
         VB ok = vi_lt(st, n);
+        if (way) {
+            if (si.status == ACMPC_SOLVED) st_idx_if(ok, way + 6 * n, st, vel[j]);
+            if (vel_out) st_idx_if(ok, vel_out, st, vel[j]);
+            continue;
+        }
         vel[j] = (si.status == ACMPC_SOLVED) ? vsel(ok, vel[j], VD(0.0)) : VD(0.0);
         st_idx_if(ok, vel_out, st, vel[j]);
         if (o.waypoints) {
@@ -1635,6 +1696,7 @@ AC_DEV void control_instance(const Ctx<C>& c, const double* raw_path, const doub
     cq.solve(ci, warm, use_warm);
     // unpack (spatial_mpc.py:193-212) and roll out (dynamics.py:42-63)
     const double L = c.cfg->wheelbase;
+    VD un[C][3];
     AC_UNROLL
     for (int j = 0; j < C; ++j) {
         VI st = c.stage(j);
@@ -1659,6 +1721,20 @@ AC_DEV void control_instance(const Ctx<C>& c, const double* raw_path, const doub
             st_idx_if(ok, o.prediction, st * 2 + 1, c.ld(F_YS, j) + ey * vcos(ps));
         }
         if (o.cum_time) st_idx_if(ok, o.cum_time, st, tt);
+        un[j][0] = ey, un[j][1] = ep, un[j][2] = tt;
+    }
+    if (o.derived) {   // spatial_mpc.py:208-211 over x_0 .. x_{n-1}: times, accelerations (sic: e_y column), steer_rates
+        VD nx[C][3];
+        pull_next_k<C, 3>(un, nx);
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VI st = c.stage(j);
+            VB ok = vi_le(st, n - 2);
+            VD dt = nx[j][2] - un[j][2];
+            st_idx_if(ok, o.derived, st, dt);
+            st_idx_if(ok, o.derived + (n - 1), st, (nx[j][0] - un[j][0]) / dt);
+            st_idx_if(ok, o.derived + 2 * (n - 1), st, (nx[j][1] - un[j][1]) / dt);
+        }
     }
     AC_LANE0
     {

@@ -31,29 +31,31 @@ constexpr int kScanPoints = 500;       // perception/utils.py:112
 // ACMPC_TRACK_RANK_DEFICIENT (degree reduced to what the abscissae determine) -- include/acmpc_b200.h
 
 // ---- remove_near_duplicate_points ---------------------------------------------------------------------------------
-__device__ __forceinline__ bool keep_point(const double* __restrict__ xy, int i, int M, double tol)
+// rows of `ld` doubles; columns 0 and 1 are (x, y), further columns (z, width ...) travel with their row like numpy's
+// track[is_not_duplicated]
+__device__ __forceinline__ bool keep_point(const double* __restrict__ xy, int i, int M, int ld, double tol)
 {
     if (i >= M) return false;
     if (i == 0) return true;
-    const double dx = xy[2 * i] - xy[2 * i - 2], dy = xy[2 * i + 1] - xy[2 * i - 1];
+    const double dx = xy[(size_t)ld * i] - xy[(size_t)ld * (i - 1)], dy = xy[(size_t)ld * i + 1] - xy[(size_t)ld * (i - 1) + 1];
     return hypot(dx, dy) > tol;      // dists > 0.0001, load.py:34 (NaN compares false, as in numpy)
 }
 
-__global__ void near_duplicate_count_kernel(const double* __restrict__ xy, int M, double tol, int* __restrict__ cta_counts)
+__global__ void near_duplicate_count_kernel(const double* __restrict__ xy, int M, int ld, double tol, int* __restrict__ cta_counts)
 {
     const int i = blockIdx.x * kDupThreads + threadIdx.x;
-    const int c = __syncthreads_count(keep_point(xy, i, M, tol));
+    const int c = __syncthreads_count(keep_point(xy, i, M, ld, tol));
     if (threadIdx.x == 0) cta_counts[blockIdx.x] = c;
 }
 
-__global__ void near_duplicate_scatter_kernel(const double* __restrict__ xy, int M, double tol,
+__global__ void near_duplicate_scatter_kernel(const double* __restrict__ xy, int M, int ld, double tol,
                                               const int* __restrict__ cta_counts, double* __restrict__ out,
                                               int* __restrict__ kept)
 {
     __shared__ int base, warp_off[kDupThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * kDupThreads + threadIdx.x;
-    const bool keep = keep_point(xy, i, M, tol);
+    const bool keep = keep_point(xy, i, M, ld, tol);
     const unsigned mask = __ballot_sync(kAll, keep);
     if (lane == 0) warp_off[warp] = __popc(mask);
     if (warp == 0) {                   // rows kept by the CTAs before this one
@@ -74,7 +76,7 @@ __global__ void near_duplicate_scatter_kernel(const double* __restrict__ xy, int
     __syncthreads();
     if (keep) {
         const int pos = base + warp_off[warp] + __popc(mask & ((1u << lane) - 1u));
-        out[2 * pos] = xy[2 * i], out[2 * pos + 1] = xy[2 * i + 1];
+        for (int c = 0; c < ld; ++c) out[(size_t)ld * pos + c] = xy[(size_t)ld * i + c];
     }
 }
 

@@ -115,6 +115,20 @@ class BatchedMPC:
         arrs["_keepalive"] = keep
         return arrs
 
+    def _check_host_outputs(self, out, B: int):
+        """A caller-supplied `out` dict hands raw pointers to the library: every array must be exactly what the
+        ABI writes (shape (B,) + field shape, dtype, C-contiguous, writeable)."""
+        spec = _capi.output_spec(self.H)
+        for name, a in out.items():
+            if name.startswith("_"):
+                continue
+            if name not in spec:
+                raise ValueError(f"unknown output field {name!r}")
+            shp, dt = spec[name]
+            if not isinstance(a, np.ndarray) or a.shape != (B,) + shp or a.dtype != np.dtype(dt) \
+                    or not a.flags.c_contiguous or not a.flags.writeable:
+                raise ValueError(f"out[{name!r}] must be a writeable C-contiguous {dt} array of shape {(B,) + shp}")
+
     def solve_host(self, paths, offsets=None, vmax=None, is_localised: bool = False, out=None, fields=None,
                    keep_warm: bool = False):
         """HOST buffers in, HOST buffers out (acmpc_solve_batch_host): H2D + kernels + D2H + sync.
@@ -131,6 +145,8 @@ class BatchedMPC:
                 raise ValueError(f"{nm} must have shape ({B},)")
         if out is None:
             out = self.alloc_host_outputs(B, fields)
+        else:
+            self._check_host_outputs(out, B)
         o = _capi.Outputs()
         for name in _capi.OUTPUT_FIELDS:
             if name in out:
@@ -140,6 +156,93 @@ class BatchedMPC:
         self._check(self._lib.acmpc_solve_batch_host(self._handle(), B, ptr(paths), ptr(offsets), ptr(vmax),
                                                      int(bool(is_localised)), int(bool(keep_warm)), C.byref(o)))
         return out
+
+    # -- stand-alone pieces of the step (cut A) --------------------------------
+    def speed_profile_host(self, waypoints, vmax=None, is_localised: bool = False, end_vel=None,
+                           keep_warm: bool = False):
+        """SpatialMPC.compute_speed_profile (spatial_mpc.py:89-123) for B ReferencePaths: `waypoints` (B,7,n) float64,
+        updated IN PLACE (velocities row of the instances whose QP is "solved").  Returns dict(x (B,n) = dec.x,
+        status, iters, rho_updates (B,))."""
+        w = waypoints
+        if not (isinstance(w, np.ndarray) and w.dtype == np.float64 and w.flags.c_contiguous and w.ndim == 3
+                and w.shape[1:] == (7, self.n)):
+            raise ValueError(f"waypoints must be a C-contiguous float64 (B, 7, {self.n}) array")
+        B = w.shape[0]
+        vmax = None if vmax is None else np.ascontiguousarray(vmax, dtype=np.float64)
+        if vmax is not None and vmax.shape != (B,):
+            raise ValueError(f"vmax must have shape ({B},)")
+        x = np.zeros((B, self.n))
+        st, it, ru = np.zeros(B, np.int32), np.zeros(B, np.int32), np.zeros(B, np.int32)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        self._check(self._lib.acmpc_speed_profile_batch_host(
+            self._handle(), B, w.ctypes.data_as(dp), None if vmax is None else vmax.ctypes.data_as(dp),
+            int(bool(is_localised)), int(end_vel is not None), float(0.0 if end_vel is None else end_vel),
+            int(bool(keep_warm)), x.ctypes.data_as(dp), st.ctypes.data_as(ip), it.ctypes.data_as(ip), ru.ctypes.data_as(ip)))
+        return dict(x=x, status=st, iters=it, rho_updates=ru)
+
+    def speed_profile_device(self, waypoints, vmax=None, is_localised: bool = False, end_vel=None, warm=None,
+                             warm_valid: bool = True, stream=None):
+        """Same with DEVICE tensors, asynchronous on `stream`: waypoints (B,7,n) float64 CUDA tensor, in place.
+        Returns dict of CUDA tensors x (B,n), status (B,), iters (B,2), rho_updates (B,2) (column 0 is written)."""
+        import torch
+
+        w = waypoints
+        if not (w.is_cuda and w.dtype == torch.float64 and w.is_contiguous() and w.dim() == 3
+                and tuple(w.shape[1:]) == (7, self.n)):
+            raise ValueError(f"waypoints must be a contiguous float64 CUDA tensor of shape (B, 7, {self.n})")
+        B = w.shape[0]
+        if vmax is not None and not (vmax.is_cuda and vmax.dtype == torch.float64 and vmax.is_contiguous() and vmax.numel() == B):
+            raise ValueError("vmax must be a contiguous float64 CUDA tensor of B elements")
+        x = torch.empty((B, self.n), dtype=torch.float64, device=w.device)
+        st = torch.empty(B, dtype=torch.int32, device=w.device)
+        it = torch.zeros((B, 2), dtype=torch.int32, device=w.device)
+        ru = torch.zeros((B, 2), dtype=torch.int32, device=w.device)
+        s = torch.cuda.current_stream(w.device) if stream is None else stream
+        self._check(self._lib.acmpc_speed_profile_batch_device(
+            self._handle(), B, w.data_ptr(), None if vmax is None else vmax.data_ptr(), int(bool(is_localised)),
+            int(end_vel is not None), float(0.0 if end_vel is None else end_vel),
+            None if warm is None else warm.data_ptr(), int(bool(warm_valid and warm is not None)), x.data_ptr(),
+            st.data_ptr(), it.data_ptr(), ru.data_ptr(), C.c_void_p(s.cuda_stream)))
+        return dict(x=x, status=st, iters=it, rho_updates=ru)
+
+    def t2s(self, waypoints, states) -> np.ndarray:
+        """SpatialBicycleModel.t2s (dynamics.py:23-40) for B (waypoint, state) pairs: (B,3), (B,3) -> (B,3)."""
+        w = np.ascontiguousarray(waypoints, dtype=np.float64)
+        x = np.ascontiguousarray(states, dtype=np.float64)
+        if w.ndim != 2 or w.shape[1] != 3 or x.shape != w.shape:
+            raise ValueError("waypoints and states must both be (B, 3)")
+        out = np.empty_like(w)
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_t2s_host(self._handle(), w.shape[0], w.ctypes.data_as(dp), x.ctypes.data_as(dp),
+                                             out.ctypes.data_as(dp)))
+        return out
+
+    def s2t(self, waypoints, states, prediction: bool = False) -> np.ndarray:
+        """SpatialBicycleModel.s2t (dynamics.py:42-63): waypoints (B,7,n), states (B,n,3) -> (B,3,n) rows X, Y, Psi;
+        prediction=True returns SpatialMPC.update_prediction's (B,n,2) instead (spatial_mpc.py:156-168)."""
+        w = np.ascontiguousarray(waypoints, dtype=np.float64)
+        x = np.ascontiguousarray(states, dtype=np.float64)
+        if w.ndim != 3 or w.shape[1] != 7 or x.shape != (w.shape[0], w.shape[2], 3):
+            raise ValueError("waypoints (B,7,n) and states (B,n,3) expected")
+        B, _, n = w.shape
+        out = np.empty((B, n, 2)) if prediction else np.empty((B, 3, n))
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_s2t_host(self._handle(), B, n, w.ctypes.data_as(dp), x.ctypes.data_as(dp),
+                                             None if prediction else out.ctypes.data_as(dp),
+                                             out.ctypes.data_as(dp) if prediction else None))
+        return out
+
+    def linearise(self, waypoints):
+        """SpatialBicycleModel.linearise (dynamics.py:65-103): waypoints (B,7,n) -> f (B,n,3), A (B,n,3,3), B (B,n,3,2)."""
+        w = np.ascontiguousarray(waypoints, dtype=np.float64)
+        if w.ndim != 3 or w.shape[1] != 7:
+            raise ValueError("waypoints (B,7,n) expected")
+        B, _, n = w.shape
+        f, A, Bm = np.empty((B, n, 3)), np.empty((B, n, 3, 3)), np.empty((B, n, 3, 2))
+        dp = C.POINTER(C.c_double)
+        self._check(self._lib.acmpc_linearise_host(self._handle(), B, n, w.ctypes.data_as(dp), f.ctypes.data_as(dp),
+                                                   A.ctypes.data_as(dp), Bm.ctypes.data_as(dp)))
+        return f, A, Bm
 
     # -- whole-track speed profile (SURVEY.md section 8f row 1) -----------------------------------
     @staticmethod
@@ -254,14 +357,16 @@ class BatchedMPC:
 
     # -- track side of the step ---------------------------------
     def remove_near_duplicate_points(self, track, tol: float = 0.0001) -> np.ndarray:
-        """utils/load.py:30-35 on the device: (M,2) -> the rows farther than `tol` from their predecessor."""
+        """utils/load.py:30-35 on the device: (M,cols>=2) -> the rows whose (x, y) = columns 0, 1 lie farther than `tol`
+        from their predecessor's; further columns travel with their row (numpy's track[is_not_duplicated])."""
         t = np.ascontiguousarray(track, dtype=np.float64)
-        if t.ndim != 2 or t.shape[1] != 2:
-            raise ValueError(f"track must be (M, 2), got {t.shape}")
+        if t.ndim != 2 or t.shape[1] < 2:
+            raise ValueError(f"track must be (M, >=2), got {t.shape}")
         out, kept = np.empty_like(t), C.c_int32(0)
         dp = C.POINTER(C.c_double)
-        self._check(self._lib.acmpc_remove_near_duplicates_host(self._handle(), t.shape[0], t.ctypes.data_as(dp), float(tol),
-                                                                out.ctypes.data_as(dp), C.byref(kept)))
+        self._check(self._lib.acmpc_remove_near_duplicates_cols_host(self._handle(), t.shape[0], t.shape[1],
+                                                                     t.ctypes.data_as(dp), float(tol),
+                                                                     out.ctypes.data_as(dp), C.byref(kept)))
         return out[:kept.value].copy()
 
     def smooth_tracks_with_polyfit(self, tracks, num_points: int, degree: int = 3, return_info: bool = False):

@@ -107,7 +107,7 @@ def centreline(track: str, map_dir: str | None = None, ds: float = 0.5) -> np.nd
 
         path = load.find_map(track, map_dir)
         if path:
-            return _resample_closed(load.track_map(path)["centre"], ds)
+            return _resample_closed(load.track_map(path)["centre"][:, :2], ds)
     return synthetic_centreline(track, ds)
 
 

@@ -45,7 +45,7 @@ def track_map(path: str, solver=None) -> Dict:
     track_dict = EXTENSION_TO_METHOD[path.split(".")[-1]](path)
     tracks = {"left": track_dict["outside_track"], "right": track_dict["inside_track"],
               "centre": track_dict["centre_track"]}
-    return {k: remove_near_duplicate_points(np.asarray(v, dtype=np.float64)[:, :2], solver) for k, v in tracks.items()}
+    return {k: remove_near_duplicate_points(np.asarray(v, dtype=np.float64), solver) for k, v in tracks.items()}
 
 
 def save_track_map(path: str, centre: np.ndarray, outside: np.ndarray, inside: np.ndarray) -> None:

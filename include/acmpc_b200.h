@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ACMPC_ABI_VERSION 1
+#define ACMPC_ABI_VERSION 2
 
 /* OSQP status codes written to status[] / status_speed[] ("solved" == 1, spatial_mpc.py:115,193) */
 #define ACMPC_SOLVED 1
@@ -69,6 +69,12 @@ typedef struct acmpc_config {
     int32_t check_termination;     /* 25 */
     int32_t adaptive_rho;          /* 1 */
     int32_t adaptive_rho_interval; /* fixed iteration interval, default 50 */
+    /* OSQP >= 1.0 termination semantics (ABI 2).  0 (default) = OSQP 0.6.x: "solved" <=> primal and dual residual
+     * tests.  1 = OSQP 1.x `check_dualgap`: additionally |x'Px + q'x + SC(y)| <= eps_abs + eps_rel * max(|x'Px|, |q'x|,
+     * |SC(y)|), SC(y) = u'max(y,0) + l'min(y,0) over the finite bounds.  requirements.txt:2 of the reference does not pin
+     * the wheel, so a maintainer may be running either; tools/pin_osqp.py reports which setting their wheel matches. */
+    int32_t check_dualgap;
+    int32_t reserved1;
 } acmpc_config;
 
 /* Result arrays, one slice per instance.  Any pointer may be NULL (field not written).
@@ -87,6 +93,8 @@ typedef struct acmpc_outputs {
     int32_t *iters;         /* [B,2]   ADMM iterations: speed QP, control QP */
     int32_t *rho_updates;   /* [B,2]   refactorisations caused by adaptive rho */
     double *waypoints;      /* [B,7,n] ReferencePath rows xs ys psis kappas distances widths velocities  reference_path */
+    double *derived;        /* [B,3,n-1] rows times = diff(t), accelerations = diff(e_y) / times (sic), steer_rates =
+                             * diff(e_psi) / times over x_0..x_{n-1}                        spatial_mpc.py:208-211 (ABI 2) */
 } acmpc_outputs;
 
 typedef struct acmpc_handle acmpc_handle;
@@ -122,7 +130,9 @@ int64_t acmpc_warm_stride(const acmpc_handle *h);
  *             internal speed-profile hand-over buffer has to grow: first call, or a larger B, with
  *             d_out->v_ref == NULL).  Calls on one handle must be stream-ordered with each other (the
  *             reference object is single-threaded): the work queue of the persistent warps
- *             is per handle. */
+ *             is per handle.  The device and the host entry points keep separate work queues and order buffers, so they
+ *             may be mixed on one handle; they still share the handle's warm-start records only through the pointers
+ *             the caller passes. */
 int32_t acmpc_solve_batch_device(acmpc_handle *h, int32_t B, const double *d_paths,
                                  const double *d_offsets, const double *d_vmax,
                                  int32_t is_localised, void *d_warm, int32_t warm_valid,
@@ -135,6 +145,39 @@ int32_t acmpc_solve_batch_device(acmpc_handle *h, int32_t B, const double *d_pat
 int32_t acmpc_solve_batch_host(acmpc_handle *h, int32_t B, const double *paths,
                                const double *offsets, const double *vmax, int32_t is_localised,
                                int32_t keep_warm, const acmpc_outputs *out);
+
+/* SpatialMPC.compute_speed_profile(reference_path, is_localised, end_vel) (spatial_mpc.py:89-123) for B ReferencePaths,
+ * the speed-profile kernel alone.  waypoints [B,7,n] rows xs ys psis kappas distances widths velocities (paths.py): the
+ * kappas and distances rows are read; the velocities row of instance b is WRITTEN ONLY when its QP is "solved" and left
+ * untouched otherwise (spatial_mpc.py:115-122).  vmax [B] = the live speed_profile_constraints["v_max"] (NULL = cfg.v_max);
+ * has_end_vel / end_vel = the call's end_vel argument (None <=> has_end_vel == 0; ignored when is_localised,
+ * speed_profile.py:131-137); the other constraints come from the handle's config.
+ * solution [B,n] (may be NULL) = dec.x whatever the status; status [B], iters [B], rho_updates [B] may be NULL.
+ * Warm start: the same records as acmpc_solve_batch_* (slot 0 = speed solver, slot 1 = localised speed solver), so a
+ * call sequence mixing get_control and compute_speed_profile on one object behaves like the reference's, which shares
+ * the two OSQP objects between them (spatial_mpc.py:43-58,101-105).
+ * _device: device pointers, asynchronous on `stream`; d_iters / d_rho_updates are [B,2] pairs like acmpc_outputs
+ * (column 0 is written).  _host: host pointers, synchronous, iters / rho_updates are [B]. */
+int32_t acmpc_speed_profile_batch_device(acmpc_handle *h, int32_t B, double *d_waypoints, const double *d_vmax,
+                                         int32_t is_localised, int32_t has_end_vel, double end_vel, void *d_warm,
+                                         int32_t warm_valid, double *d_solution, int32_t *d_status, int32_t *d_iters,
+                                         int32_t *d_rho_updates, void *stream);
+int32_t acmpc_speed_profile_batch_host(acmpc_handle *h, int32_t B, double *waypoints, const double *vmax,
+                                       int32_t is_localised, int32_t has_end_vel, double end_vel, int32_t keep_warm,
+                                       double *solution, int32_t *status, int32_t *iters, int32_t *rho_updates);
+
+/* SpatialBicycleModel as stand-alone batched calls (inside a step these are fused into the control kernel):
+ *   acmpc_t2s_host        dynamics.py:23-40   waypoints[B,3] = (x, y, psi) of the reference waypoint, states[B,3] = (x, y,
+ *                                             psi) of the vehicle -> out[B,3] = (e_y, e_psi wrapped to [-pi, pi), t = 0)
+ *   acmpc_s2t_host        dynamics.py:42-63   waypoints[B,7,n], states[B,n,3] -> out[B,3,n] rows X, Y, Psi (may be NULL);
+ *                                             prediction[B,n,2] (may be NULL) = SpatialMPC.update_prediction =
+ *                                             s2t(...)[:-1].T (spatial_mpc.py:156-168)
+ *   acmpc_linearise_host  dynamics.py:65-103  waypoints[B,7,n] -> f[B,n,3], A[B,n,3,3], Bm[B,n,3,2] (each may be NULL) */
+int32_t acmpc_t2s_host(acmpc_handle *h, int32_t B, const double *waypoints, const double *states, double *out);
+int32_t acmpc_s2t_host(acmpc_handle *h, int32_t B, int32_t n, const double *waypoints, const double *states, double *out,
+                       double *prediction);
+int32_t acmpc_linearise_host(acmpc_handle *h, int32_t B, int32_t n, const double *waypoints, double *f, double *A,
+                             double *Bm);
 
 /* Counters of the last call: kernel launches issued (per chunk: speed-profile kernel + control kernel, plus the
  * small ordering kernel for batches of 1024+ with per-instance v_max; the host entry point splits batches of
@@ -226,6 +269,10 @@ int32_t acmpc_select_commands_f64_host(acmpc_handle *h, int32_t B, int32_t n, co
  * INPUT exceeds tol (the reference uses 0.0001), order preserved.  xy[M,2] -> out[*kept,2]; `out` needs room for M rows. */
 int32_t acmpc_remove_near_duplicates_host(acmpc_handle *h, int32_t M, const double *xy, double tol, double *out,
                                           int32_t *kept);
+/* Same for rows of `cols` >= 2 doubles whose first two columns are (x, y): whole rows are kept or dropped, like numpy's
+ * track[is_not_duplicated] on a map with extra columns (z, width ...). */
+int32_t acmpc_remove_near_duplicates_cols_host(acmpc_handle *h, int32_t M, int32_t cols, const double *rows, double tol,
+                                               double *out, int32_t *kept);
 
 /* perception/utils.py:107-119 smooth_track_with_polyfit(track, num_points, degree) for B tracks at once.
  * Track b = rows offsets[b] .. offsets[b+1] of points[.,2] (x, y); offsets[0] == 0; an empty track yields the

@@ -59,6 +59,7 @@ static void port_settings(const acmpc_config *c, opq_settings *s)
     s->check_termination = c->check_termination;
     s->adaptive_rho = c->adaptive_rho, s->adaptive_rho_interval = c->adaptive_rho_interval;
     s->warm_start = 1;
+    s->check_dualgap = c->check_dualgap;
 }
 
 /* spatial_mpc.py:125-154 */
@@ -323,6 +324,13 @@ int acmpc_port_step(acmpc_port *p, const double *path, double offset, double v_m
         }
     if (o->cum_time)
         for (int k = 0; k < n; k++) o->cum_time[k] = x[3 * k + 2];
+    if (o->derived)   /* spatial_mpc.py:208-211: times, accelerations (sic: e_y column), steer_rates */
+        for (int k = 0; k + 1 < n; k++) {
+            double dt = x[3 * (k + 1) + 2] - x[3 * k + 2];
+            o->derived[k] = dt;
+            o->derived[(n - 1) + k] = (x[3 * (k + 1)] - x[3 * k]) / dt;
+            o->derived[2 * (n - 1) + k] = (x[3 * (k + 1) + 1] - x[3 * k + 1]) / dt;
+        }
     if (o->states) memcpy(o->states, x, sizeof(double) * (size_t)(3 * H));
     if (o->v_ref) memcpy(o->v_ref, vel, sizeof(double) * (size_t)n);
     if (o->waypoints) memcpy(o->waypoints, wp, sizeof(double) * (size_t)(7 * n));
@@ -334,6 +342,30 @@ int acmpc_port_step(acmpc_port *p, const double *path, double offset, double v_m
     if (o->iters) o->iters[0] = si.iter, o->iters[1] = ci.iter;
     if (o->rho_updates) o->rho_updates[0] = si.rho_updates, o->rho_updates[1] = ci.rho_updates;
     return 0;
+}
+
+/* SpatialMPC.compute_speed_profile(reference_path, is_localised, end_vel) (spatial_mpc.py:89-123) on the object's
+ * persistent speed solvers: `wp` (7,n) ReferencePath rows, velocities row written only when "solved".
+ * has_end_vel / end_vel = the call's end_vel argument (None <=> has_end_vel == 0). */
+int acmpc_port_speed_profile(acmpc_port *p, double *wp, double v_max_live, int is_localised, int has_end_vel,
+                             double end_vel, int warm, double *x_out, int *iters, int *rho_updates)
+{
+    int n = p->n, loc = is_localised ? 1 : 0;
+    opq_settings st;
+    opq_info si;
+    port_settings(&p->cfg, &st);
+    int he = p->cfg.has_end_velocity;
+    double ev = p->cfg.end_velocity;
+    p->cfg.has_end_velocity = has_end_vel, p->cfg.end_velocity = end_vel;
+    assemble_speed_qp(p, wp, v_max_live, loc);
+    p->cfg.has_end_velocity = he, p->cfg.end_velocity = ev;
+    int sstat = solve_ws(&p->speed_ws[loc], &st, warm, p->sn, p->sm, p->sPp, p->sPi, p->sPx, p->sq,
+                         p->sAp, p->sAi, p->sAx, p->sl, p->su, p->sx, &si);
+    if (sstat == OPQ_SOLVED) memcpy(wp + 6 * n, p->sx, sizeof(double) * (size_t)n);
+    if (x_out) memcpy(x_out, p->sx, sizeof(double) * (size_t)n);
+    if (iters) *iters = si.iter;
+    if (rho_updates) *rho_updates = si.rho_updates;
+    return sstat;
 }
 
 /* introspection for the assembly tests: the QP data of the last step */
@@ -395,6 +427,7 @@ static void *batch_worker(void *arg)
             if (out->iters) o.iters = out->iters + (size_t)b * 2;
             if (out->rho_updates) o.rho_updates = out->rho_updates + (size_t)b * 2;
             if (out->waypoints) o.waypoints = out->waypoints + (size_t)b * 7 * n;
+            if (out->derived) o.derived = out->derived + (size_t)b * 3 * (n - 1);
             acmpc_port_step(p, j->paths + (size_t)b * 3 * H, j->offsets ? j->offsets[b] : 0.0,
                             j->vmax ? j->vmax[b] : j->cfg->v_max, j->is_localised, 0, &o);
         }

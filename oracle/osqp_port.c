@@ -57,6 +57,7 @@ struct opq_workspace {
     /* info */
     opq_info info;
     int rho_updates;
+    double xtPx, qtx, sc;   /* scaled x'Px, q'x, SC(y) of the last update_info (check_dualgap) */
 };
 
 void opq_default_settings(opq_settings *s)
@@ -76,6 +77,7 @@ void opq_default_settings(opq_settings *s)
     s->adaptive_rho_interval = 50;
     s->warm_start = 1;
     s->scaled_termination = 0;
+    s->check_dualgap = 0;
 }
 
 const char *opq_status_string(int status)
@@ -651,6 +653,20 @@ static void update_info(opq_workspace *w, int iter)
     w->info.obj_val = compute_obj_val(w);
     w->info.pri_res = w->m ? compute_pri_res(w) : 0.0;
     w->info.dua_res = compute_dua_res(w);
+    if (w->s.check_dualgap) {
+        /* OSQP 1.x compute_obj_val_dual_gap: SC(y) = u'max(y,0) + l'min(y,0); sides beyond OSQP_INFTY * MIN_SCALING
+         * are infinite bounds and contribute nothing */
+        const double big = OPQ_INFTY * OPQ_MIN_SCALING;
+        double a = 0.0, b = 0.0, sc = 0.0;
+        for (int j = 0; j < w->n; j++) a += w->Pxv[j] * w->x[j], b += w->q[j] * w->x[j];
+        for (int i = 0; i < w->m; i++) {
+            double y = w->y[i];
+            if (w->u[i] < big && y > 0.0) sc += w->u[i] * y;
+            if (w->l[i] > -big && y < 0.0) sc += w->l[i] * y;
+        }
+        w->xtPx = a, w->qtx = b, w->sc = sc;
+        w->info.duality_gap = (a + b + sc) * (w->s.scaling ? w->cinv : 1.0);
+    }
 }
 
 static double pri_tol(const opq_workspace *w, double eps_abs, double eps_rel)
@@ -756,7 +772,7 @@ static int check_termination(opq_workspace *w, int approximate)
 {
     double eps_abs = w->s.eps_abs, eps_rel = w->s.eps_rel;
     double eps_pinf = w->s.eps_prim_inf, eps_dinf = w->s.eps_dual_inf;
-    int prim_ok = 0, dual_ok = 0, prim_inf = 0, dual_inf = 0;
+    int prim_ok = 0, dual_ok = 0, prim_inf = 0, dual_inf = 0, gap_ok = 1;
     if (w->info.pri_res > OPQ_INFTY || w->info.dua_res > OPQ_INFTY) {
         w->info.status = OPQ_NON_CVX;
         w->info.obj_val = NAN;
@@ -772,7 +788,15 @@ static int check_termination(opq_workspace *w, int approximate)
     if (w->info.dua_res < dua_tol(w, eps_abs, eps_rel)) dual_ok = 1;
     else dual_inf = is_dual_infeasible(w, eps_dinf);
 
-    if (prim_ok && dual_ok) {
+    if (w->s.check_dualgap) {
+        double rel = fabs(w->xtPx), t = fabs(w->qtx);
+        if (t > rel) rel = t;
+        t = fabs(w->sc);
+        if (t > rel) rel = t;
+        if (w->s.scaling) rel *= w->cinv;
+        gap_ok = fabs(w->info.duality_gap) < eps_abs + eps_rel * rel;
+    }
+    if (prim_ok && dual_ok && gap_ok) {
         w->info.status = approximate ? OPQ_SOLVED_INACCURATE : OPQ_SOLVED;
         return 1;
     }

@@ -59,6 +59,8 @@ typedef struct {
     int adaptive_rho_interval; /* fixed interval; OSQP's 0 = "timing based" is not reproducible */
     int warm_start;            /* 1: keep x,z,y between solves (OSQP default) */
     int scaled_termination;    /* 0 */
+    int check_dualgap;         /* 0 = OSQP 0.6.x termination; 1 = OSQP 1.x adds the duality-gap test (restated from the
+                                  1.0 sources as remembered -- UNVERIFIED until tools/pin_osqp.py meets a 1.x wheel) */
 } opq_settings;
 
 typedef struct {
@@ -66,6 +68,7 @@ typedef struct {
     int iter;
     int rho_updates;
     double obj_val, pri_res, dua_res, rho_estimate;
+    double duality_gap;        /* x'Px + q'x + SC(y), unscaled (only meaningful with check_dualgap) */
 } opq_info;
 
 typedef struct opq_workspace opq_workspace;

@@ -55,7 +55,7 @@ class Settings(C.Structure):
         ("adaptive_rho_tolerance", C.c_double),
         ("scaling", C.c_int), ("max_iter", C.c_int), ("check_termination", C.c_int),
         ("adaptive_rho", C.c_int), ("adaptive_rho_interval", C.c_int),
-        ("warm_start", C.c_int), ("scaled_termination", C.c_int),
+        ("warm_start", C.c_int), ("scaled_termination", C.c_int), ("check_dualgap", C.c_int),
     ]
 
 
@@ -63,7 +63,7 @@ class Info(C.Structure):
     _fields_ = [
         ("status", C.c_int), ("iter", C.c_int), ("rho_updates", C.c_int),
         ("obj_val", C.c_double), ("pri_res", C.c_double), ("dua_res", C.c_double),
-        ("rho_estimate", C.c_double),
+        ("rho_estimate", C.c_double), ("duality_gap", C.c_double),
     ]
 
 
@@ -84,6 +84,7 @@ class Config(C.Structure):
         ("adaptive_rho_tolerance", C.c_double),
         ("scaling", C.c_int32), ("check_termination", C.c_int32),
         ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32),
+        ("check_dualgap", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -95,7 +96,7 @@ class Outputs(C.Structure):
         ("states", C.c_void_p), ("v_ref", C.c_void_p), ("cost", C.c_void_p),
         ("pri_res", C.c_void_p), ("dua_res", C.c_void_p), ("status", C.c_void_p),
         ("status_speed", C.c_void_p), ("iters", C.c_void_p), ("rho_updates", C.c_void_p),
-        ("waypoints", C.c_void_p),
+        ("waypoints", C.c_void_p), ("derived", C.c_void_p),
     ]
 
 
@@ -131,6 +132,9 @@ def lib() -> C.CDLL:
         L.acmpc_port_solve_batch.argtypes = [C.POINTER(Config), C.c_int, dp, dp, dp, C.c_int, C.c_int, C.POINTER(Outputs)]
         L.acmpc_port_solve_batch.restype = C.c_int
         L.acmpc_port_default_config.argtypes = [C.POINTER(Config)]
+        L.acmpc_port_speed_profile.argtypes = [C.c_void_p, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, dp,
+                                               ip, ip]
+        L.acmpc_port_speed_profile.restype = C.c_int
         L.acmpc_port_waypoints.restype = dp
         L.acmpc_port_waypoints.argtypes = [C.c_void_p]
         L.acmpc_port_get_qp.argtypes = [C.c_void_p, C.c_int, ip, ip, C.POINTER(ip), C.POINTER(ip),
@@ -252,6 +256,7 @@ OUTPUT_SPEC = {
     "iters": (lambda H, n: (2,), np.int32),
     "rho_updates": (lambda H, n: (2,), np.int32),
     "waypoints": (lambda H, n: (7, n), np.float64),
+    "derived": (lambda H, n: (3, n - 1), np.float64),
 }
 
 
@@ -287,6 +292,19 @@ class PortMPC:
                               float(self.cfg.v_max if v_max is None else v_max),
                               int(bool(is_localised)), int(bool(warm)), C.byref(o))
         return {k: v[0] for k, v in arrs.items()}
+
+    def speed_profile(self, waypoints, v_max=None, is_localised=False, end_vel=None, warm=True):
+        """compute_speed_profile (spatial_mpc.py:89-123) on this object's persistent speed solvers: `waypoints`
+        (7,n) is updated IN PLACE (velocities row only when "solved").  Returns dict(status, x, iters, rho_updates)."""
+        w = waypoints
+        assert w.dtype == np.float64 and w.flags.c_contiguous and w.shape == (7, self.H - 1)
+        x = np.zeros(self.H - 1)
+        it, ru = C.c_int(), C.c_int()
+        st = lib().acmpc_port_speed_profile(self._p, _dptr(w), float(self.cfg.v_max if v_max is None else v_max),
+                                            int(bool(is_localised)), int(end_vel is not None),
+                                            float(0.0 if end_vel is None else end_vel), int(bool(warm)), _dptr(x),
+                                            C.byref(it), C.byref(ru))
+        return dict(status=int(st), x=x, iters=it.value, rho_updates=ru.value)
 
     def waypoints(self) -> np.ndarray:
         n = self.H - 1
@@ -377,6 +395,46 @@ def reference_speeds(velocities, behind: int = 25, ahead: int = 75):
     n = len(sm)
     idx = (np.arange(n)[:, None] + np.arange(-behind, ahead)[None, :])
     return sm, np.mean(sm.take(idx, mode="wrap"), axis=1)
+
+
+# ---- SpatialBicycleModel (dynamics.py:23-103) and update_prediction (spatial_mpc.py:156-168) ------------------
+def t2s(reference_waypoint, reference_state):
+    """dynamics.py:23-40: (x, y, psi) of the waypoint and of the vehicle -> (e_y, e_psi, t = 0)."""
+    rx, ry, rpsi = reference_waypoint
+    x, y, psi = reference_state
+    e_y = np.cos(rpsi) * (y - ry) - np.sin(rpsi) * (x - rx)
+    e_psi = np.mod(psi - rpsi + np.pi, 2 * np.pi) - np.pi
+    return np.array([e_y, e_psi, 0.0])
+
+
+def s2t(waypoints, states):
+    """dynamics.py:42-63: ReferencePath rows (7,n) and spatial states (n,3) -> (3,n) rows X, Y, Psi."""
+    w, s = np.asarray(waypoints), np.asarray(states)
+    return np.array([w[0] - s[:, 0] * np.sin(w[2]), w[1] + s[:, 0] * np.cos(w[2]), w[2] + s[:, 1]])
+
+
+def update_prediction(waypoints, states):
+    """spatial_mpc.py:156-168: s2t(...)[:-1].T = (n,2) rows (X, Y)."""
+    return s2t(waypoints, states)[:-1].T
+
+
+def linearise(waypoints):
+    """dynamics.py:65-103: (7,n) rows -> f (n,3), A (n,3,3), B (n,3,2)."""
+    w = np.asarray(waypoints)
+    ka, d, v = w[3], w[4], w[6]
+    n = w.shape[1]
+    eps = 1e-12
+    A, B, f = np.zeros((n, 3, 3)), np.zeros((n, 3, 2)), np.zeros((n, 3))
+    A[:, 0, 0] = 1.0
+    A[:, 0, 1] = d
+    A[:, 1, 0] = -(ka ** 2) * d
+    A[:, 1, 1] = 1.0
+    A[:, 2, 0] = -ka / (v * d + eps)
+    A[:, 2, 2] = 1.0
+    B[:, 1, 1] = d
+    B[:, 2, 0] = -1 / (v ** 2 * d + eps)
+    f[:, 2] = 1 / (v * d + eps)
+    return f, A, B
 
 
 # ---- caller side of the step (SURVEY.md section 8f row 2) ----------------------------------------------------

@@ -19,7 +19,8 @@ def golden_batches():
             if not m.any():
                 continue
             want = {k: d[k][m] for k in ("status", "status_speed", "iters", "rho_updates", "controls", "prediction",
-                                         "cum_time", "v_ref", "cost", "dec_x", "waypoints", "pri_res", "dua_res")}
+                                         "cum_time", "v_ref", "cost", "dec_x", "waypoints", "pri_res", "dua_res",
+                                         "times", "accelerations", "steer_rates")}
             yield f"{group}-loc{flag}", kw, d["paths"][m], offs[m], vmax[m], bool(flag), want
 
 
@@ -36,5 +37,11 @@ def assert_matches_golden(got, want, H, atol):
     np.testing.assert_allclose(got["cost"], want["cost"], rtol=atol, atol=atol)
     for k in ("controls", "prediction", "cum_time", "v_ref", "waypoints"):
         np.testing.assert_allclose(got[k][ok], want[k][ok], rtol=0, atol=atol, err_msg=k)
+    # spatial_mpc.py:208-211 by VALUE: times = diff(t), accelerations = diff(e_y) / times (sic), steer_rates =
+    # diff(e_psi) / times.  Quotients of differences of quantities held to `atol`: the divisor is ~0.02-0.1 s
+    # and the differences lose up to 3 digits, so the bar is 1e3 * atol relative-or-absolute (measured: ~1e-9)
+    if "derived" in got:
+        for row, k in enumerate(("times", "accelerations", "steer_rates")):
+            np.testing.assert_allclose(got["derived"][ok][:, row], want[k][ok], rtol=1e3 * atol, atol=1e3 * atol, err_msg=k)
     np.testing.assert_allclose(got["pri_res"], want["pri_res"], rtol=1e-6, atol=atol)
     np.testing.assert_allclose(got["dua_res"], want["dua_res"], rtol=1e-6, atol=atol)

@@ -43,3 +43,25 @@ def solve_batch(cfg, paths, offsets=None, vmax=None, is_localised=False, warm=No
                                       int(bool(is_localised)), C.byref(o), port._dptr(warm), int(bool(use_warm)))
     assert rc == 0
     return arrs
+
+
+def speed_profile(cfg, waypoints, vmax=None, is_localised=False, end_vel=None, warm=None, use_warm=True):
+    """speed_instance's stand-alone mode (SpatialMPC.compute_speed_profile) on (B,7,n) rows, in place."""
+    import copy
+
+    w = waypoints
+    assert w.dtype == np.float64 and w.flags.c_contiguous and w.ndim == 3
+    B, n = w.shape[0], w.shape[2]
+    cfg = copy.copy(cfg)
+    cfg.has_end_velocity, cfg.end_velocity = int(end_vel is not None), float(0.0 if end_vel is None else end_vel)
+    vmax = None if vmax is None else np.ascontiguousarray(vmax, dtype=np.float64)
+    x = np.zeros((B, n))
+    st, it, ru = (np.zeros(B, np.intc) for _ in range(3))
+    ip = C.POINTER(C.c_int)
+    L = lib()
+    L.acmpc_emul_speed_profile.argtypes = [C.POINTER(port.Config), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                           C.c_int, C.POINTER(C.c_double), ip, ip, ip, C.POINTER(C.c_double), C.c_int]
+    L.acmpc_emul_speed_profile(C.byref(cfg), B, port._dptr(w), port._dptr(vmax), int(bool(is_localised)), port._dptr(x),
+                               st.ctypes.data_as(ip), it.ctypes.data_as(ip), ru.ctypes.data_as(ip), port._dptr(warm),
+                               int(bool(use_warm)))
+    return dict(x=x, status=st, iters=it, rho_updates=ru)

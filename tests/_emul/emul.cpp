@@ -44,6 +44,7 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
         o.iters = out->iters ? out->iters + (size_t)b * 2 : nullptr;
         o.rho_updates = out->rho_updates ? out->rho_updates + (size_t)b * 2 : nullptr;
         o.waypoints = out->waypoints ? out->waypoints + (size_t)b * 7 * n : nullptr;
+        o.derived = out->derived ? out->derived + (size_t)b * 3 * (n - 1) : nullptr;
         // the two phases are two kernels in the product; the hand-over is the speed profile
         double* wrec = warm ? warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;
         acmpc::speed_instance<C>(c, raw, vmax ? vmax[b] : cfg->v_max, is_localised, vel, o, wrec, use_warm != 0);
@@ -56,7 +57,44 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
     free(vel);
 }
 
+// stand-alone speed profile on ReferencePath rows (speed_instance's `way` mode)
+template <int C>
+void run_speed(const acmpc_config* cfg, int B, double* way, const double* vmax, int is_localised, double* sol, int* status,
+               int* iters, int* rho_updates, double* warm, int use_warm)
+{
+    const int H = cfg->horizon, n = H - 1;
+    const size_t nd = (size_t)acmpc::Layout<C>::kSpeedDoubles;
+    double* smem = (double*)malloc(sizeof(double) * nd);
+    for (int b = 0; b < B; ++b) {
+        memset(smem, 0xff, sizeof(double) * nd);
+        acmpc::Ctx<C> c;
+        c.S = nullptr, c.W = smem, c.tm.p = nullptr, c.H = H, c.n = n, c.cfg = cfg;
+        c.lane = acmpc::lane_iota();
+        acmpc::InstanceOut o;
+        memset(&o, 0, sizeof(o));
+        int32_t it2[2] = {0, 0}, ru2[2] = {0, 0}, st = 0;
+        o.status_speed = &st, o.iters = it2, o.rho_updates = ru2;
+        double* wrec = warm ? warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;
+        acmpc::speed_instance<C>(c, nullptr, vmax ? vmax[b] : cfg->v_max, is_localised, sol ? sol + (size_t)b * n : nullptr, o,
+                                 wrec, use_warm != 0, way + (size_t)b * 7 * n);
+        status[b] = st, iters[b] = it2[0], rho_updates[b] = ru2[0];
+    }
+    free(smem);
+}
+
 }  // namespace
+
+extern "C" int acmpc_emul_speed_profile(const acmpc_config* cfg, int B, double* way, const double* vmax, int is_localised,
+                                        double* sol, int* status, int* iters, int* rho_updates, double* warm, int use_warm)
+{
+    switch ((cfg->horizon + 31) / 32) {
+        case 1: run_speed<1>(cfg, B, way, vmax, is_localised, sol, status, iters, rho_updates, warm, use_warm); break;
+        case 2: run_speed<2>(cfg, B, way, vmax, is_localised, sol, status, iters, rho_updates, warm, use_warm); break;
+        case 3: run_speed<3>(cfg, B, way, vmax, is_localised, sol, status, iters, rho_updates, warm, use_warm); break;
+        default: run_speed<4>(cfg, B, way, vmax, is_localised, sol, status, iters, rho_updates, warm, use_warm); break;
+    }
+    return 0;
+}
 
 extern "C" int acmpc_emul_warm_doubles(int H)
 {

@@ -86,6 +86,10 @@ def run_case(mpc, path, is_localised, offset, v_max):
         cum_time=np.array(mpc.cum_time) if solved else np.full(n, np.nan),
         v_ref=np.array(mpc.reference_path.velocities) if solved else np.full(n, np.nan),
         infeasibility_delta=mpc.infeasibility_counter - before,
+        # spatial_mpc.py:208-211 (accelerations: sic, diff of the e_y column)
+        times=np.array(mpc.times) if solved else np.full(n - 1, np.nan),
+        accelerations=np.array(mpc.accelerations) if solved else np.full(n - 1, np.nan),
+        steer_rates=np.array(mpc.steer_rates) if solved else np.full(n - 1, np.nan),
     )
     if solved:
         rec["waypoints"] = np.array(mpc.reference_path._reference_path)
@@ -157,6 +161,53 @@ def main():
         assert abs(s["P"] - __import__("scipy.sparse", fromlist=["x"]).diags(s["P"].diagonal())).sum() == 0
         for k in ("q", "l", "u"):
             out[f"qp_{name}/{k}"] = s[k]
+    # (f) cut A of the boundary called stand-alone: compute_speed_profile on ONE object through a
+    # sequence that mixes it with get_control (the speed solvers are shared, spatial_mpc.py:101-105), and the
+    # SpatialBicycleModel methods t2s / s2t / linearise + update_prediction on the resulting paths
+    mpc = build_mpc(tracks.racing_config("monza", 50), veh)
+    P = out["racing_monza/paths"]
+    seq = [("speed", 0, False, 14.0), ("speed", 1, False, None), ("step", 2, False, None), ("speed", 3, True, 9.0),
+           ("speed", 4, False, 11.5), ("step", 5, True, None), ("speed", 0, True, None), ("speed", 2, False, 14.0)]
+    rng = np.random.default_rng(77)
+    rec = {k: [] for k in ("kind", "path_index", "localised", "end_vel", "vmax", "way_in", "way_out", "x", "status", "iters",
+                           "rho_updates", "t2s_state", "t2s_out", "s2t_states", "s2t_out", "pred_out", "lin_f", "lin_A",
+                           "lin_B")}
+    for kind, pi, loc, ev in seq:
+        vm = float(rng.uniform(30, 84))
+        mpc.speed_profile_constraints["v_max"] = vm
+        del osqp._RECORD[:]
+        rec["kind"].append(0 if kind == "speed" else 1), rec["path_index"].append(pi), rec["localised"].append(int(loc))
+        rec["end_vel"].append(np.nan if ev is None else ev), rec["vmax"].append(vm)
+        if kind == "step":
+            mpc.get_control(P[pi], loc, 0.0)
+            sp = [r for k, r in osqp._RECORD if k == "solve"][0]
+            z = np.zeros((7, 49))
+            for k in ("way_in", "way_out"):
+                rec[k].append(z)
+            rec["x"].append(sp["x"]), rec["status"].append(sp["status_val"]), rec["iters"].append(sp["iter"])
+            rec["rho_updates"].append(sp["rho_updates"])
+            for k in ("t2s_state", "t2s_out"):
+                rec[k].append(np.zeros(3))
+            rec["s2t_states"].append(np.zeros((49, 3))), rec["s2t_out"].append(np.zeros((3, 49)))
+            rec["pred_out"].append(np.zeros((49, 2))), rec["lin_f"].append(np.zeros((49, 3)))
+            rec["lin_A"].append(np.zeros((49, 3, 3))), rec["lin_B"].append(np.zeros((49, 3, 2)))
+            continue
+        rp = mpc.construct_waypoints(P[pi])
+        rp.velocities = np.full(49, 5.0 + pi)          # must survive a failed solve untouched
+        rec["way_in"].append(np.array(rp._reference_path))
+        rp = mpc.compute_speed_profile(rp, loc, end_vel=ev)
+        sp = [r for k, r in osqp._RECORD if k == "solve"][0]
+        rec["way_out"].append(np.array(rp._reference_path))
+        rec["x"].append(sp["x"]), rec["status"].append(sp["status_val"]), rec["iters"].append(sp["iter"])
+        rec["rho_updates"].append(sp["rho_updates"])
+        state = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), np.pi / 2 + rng.uniform(-3.5, 3.5)])
+        rec["t2s_state"].append(state), rec["t2s_out"].append(mpc.model.t2s(rp.get_state(0), state))
+        xs = np.column_stack([rng.uniform(-2, 2, 49), rng.uniform(-0.3, 0.3, 49), np.cumsum(rng.uniform(0.01, 0.1, 49))])
+        rec["s2t_states"].append(xs), rec["s2t_out"].append(mpc.model.s2t(rp, xs))
+        rec["pred_out"].append(mpc.update_prediction(xs, rp))
+        f, A, Bm = mpc.model.linearise(rp)
+        rec["lin_f"].append(f), rec["lin_A"].append(A), rec["lin_B"].append(Bm)
+    out.update({f"cut_a/{k}": np.array(v) for k, v in rec.items()})
     np.savez_compressed(os.path.join(HERE, "mpc_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "mpc_golden.npz"), len(out), "arrays")
     for g in sorted({k.split("/")[0] for k in out}):

@@ -31,7 +31,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert set(declared) == set(_capi.EXPORTED)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-    assert lib.acmpc_abi_version() == 1
+    assert lib.acmpc_abi_version() == 2
 
 
 def test_config_struct_layout_matches_the_header_defaults():

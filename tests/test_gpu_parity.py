@@ -164,7 +164,10 @@ def test_drop_in_spatial_mpc_get_control_matches_reference_attributes():
             np.testing.assert_allclose(mpc.current_prediction, g["prediction"][b], rtol=0, atol=TOL)
             np.testing.assert_allclose(mpc.cum_time, g["cum_time"][b], rtol=0, atol=TOL)
             np.testing.assert_allclose(mpc.reference_path.velocities, g["v_ref"][b], rtol=0, atol=TOL)
-            assert mpc.times.shape == (48,) and mpc.accelerations.shape == (48,) and mpc.steer_rates.shape == (48,)
+            # spatial_mpc.py:208-211 by value, against the reference's own attributes
+            np.testing.assert_allclose(mpc.times, g["times"][b], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(mpc.accelerations, g["accelerations"][b], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(mpc.steer_rates, g["steer_rates"][b], rtol=1e-5, atol=1e-5)
 
 
 def _assert_equals_oracle(got, want, fields=("controls", "states", "v_ref", "cost", "prediction", "cum_time")):
@@ -325,7 +328,10 @@ def test_large_batch_131072_instances():
 SETTINGS = [dict(scaling=0), dict(scaling=3), dict(check_termination=1), dict(check_termination=10),
             dict(check_termination=7, adaptive_rho_interval=20), dict(adaptive_rho=0), dict(adaptive_rho_interval=25),
             dict(alpha=1.0), dict(rho=1.0), dict(eps_abs=1e-5, eps_rel=1e-5), dict(max_iter=60), dict(max_iter=1),
-            dict(check_termination=0, max_iter=80)]
+            dict(check_termination=0, max_iter=80),
+            # OSQP 1.x termination semantics (duality-gap test on top of the residual tests), alone and combined
+            dict(check_dualgap=1), dict(check_dualgap=1, eps_abs=1e-5, eps_rel=1e-5), dict(check_dualgap=1, scaling=0),
+            dict(check_dualgap=1, adaptive_rho_interval=25, check_termination=5)]
 
 
 @pytest.mark.parametrize("kw", SETTINGS, ids=[",".join(f"{k}={v}" for k, v in s.items()) for s in SETTINGS])

@@ -76,7 +76,10 @@ def test_warm_batch_matches_oracle_sequences_with_mixed_localisation():
 SETTINGS = [dict(), dict(scaling=0), dict(scaling=3), dict(check_termination=1), dict(check_termination=10),
             dict(check_termination=7, adaptive_rho_interval=20), dict(adaptive_rho=0), dict(adaptive_rho_interval=25),
             dict(alpha=1.0), dict(rho=1.0), dict(eps_abs=1e-5, eps_rel=1e-5), dict(max_iter=60), dict(max_iter=1),
-            dict(check_termination=0, max_iter=80)]
+            dict(check_termination=0, max_iter=80),
+            # OSQP 1.x termination semantics (duality-gap test on top of the residual tests), alone and combined
+            dict(check_dualgap=1), dict(check_dualgap=1, eps_abs=1e-5, eps_rel=1e-5), dict(check_dualgap=1, scaling=0),
+            dict(check_dualgap=1, adaptive_rho_interval=25, check_termination=5)]
 
 
 @pytest.mark.parametrize("kw", SETTINGS, ids=[",".join(f"{k}={v}" for k, v in s.items()) or "default" for s in SETTINGS])
