@@ -15,6 +15,8 @@ def load():
     if not _CACHE:
         with np.load(_PATH) as z:
             for k in z.files:
+                if k.startswith("meta/"):
+                    continue
                 g, name = k.split("/")
                 _CACHE.setdefault(g, {})[name] = z[k]
     return _CACHE

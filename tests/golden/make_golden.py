@@ -18,9 +18,17 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle", "shim"), "/root/reference/src"]
+REFERENCE_SRC = os.environ.get("ACMPC_REFERENCE_SRC", "/root/reference/src")
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle", "shim"), REFERENCE_SRC]
 
-import osqp  # noqa: E402  (the shim)
+from oracle import osqp_select  # noqa: E402
+
+# The committed fixtures are made on the oracle's OSQP restatement (reproducible bit for bit in this container).
+# tools/pin_osqp.py imports this module with ACMPC_GOLDEN_SOLVER=real to run the SAME cases on a real `osqp` wheel
+# (explicit adaptive_rho_interval=50, see oracle/osqp_select.py) and writes tests/golden/osqp_pin.npz next to them.
+osqp, SOLVER_LABEL = osqp_select.select(prefer_real=os.environ.get("ACMPC_GOLDEN_SOLVER") == "real",
+                                        **({"check_dualgap": False} if os.environ.get("ACMPC_PIN_NO_DUALGAP") else {}))
+osqp_select.install(osqp)
 from ace.steering import SteeringGeometry  # noqa: E402
 from acmpc.control.controller import build_mpc  # noqa: E402
 from acmpc.control.utils import (  # noqa: E402
@@ -102,8 +110,9 @@ def stack(recs):
     return {k: np.array([r[k] for r in recs]) for k in recs[0]}
 
 
-def main():
-    out = {}
+def generate():
+    """Every case group -> dict of arrays ("group/name").  Runs on whichever `osqp` module was selected above."""
+    out = {"meta/solver": np.array(SOLVER_LABEL)}
     veh = SteeringGeometry()
     # (a) the reference's own fixture grid, cold start (fresh objects per case)
     paths = fixture_paths()
@@ -208,8 +217,15 @@ def main():
         f, A, Bm = mpc.model.linearise(rp)
         rec["lin_f"].append(f), rec["lin_A"].append(A), rec["lin_B"].append(Bm)
     out.update({f"cut_a/{k}": np.array(v) for k, v in rec.items()})
+    return out
+
+
+def main():
+    out = generate()
+    if SOLVER_LABEL != osqp_select.PORT_LABEL:
+        sys.exit("make_golden.py writes the port-generated fixtures; use tools/pin_osqp.py to run the cases on " + SOLVER_LABEL)
     np.savez_compressed(os.path.join(HERE, "mpc_golden.npz"), **out)
-    print("wrote", os.path.join(HERE, "mpc_golden.npz"), len(out), "arrays")
+    print("wrote", os.path.join(HERE, "mpc_golden.npz"), len(out), "arrays, solver:", SOLVER_LABEL)
     for g in sorted({k.split("/")[0] for k in out}):
         if f"{g}/status" in out:
             print(g, "status", out[f"{g}/status"].tolist(), "iters", out[f"{g}/iters"].tolist())
