@@ -1,0 +1,282 @@
+"""Product-level multi-GPU call: one process per GPU, a global batch of independent MPC
+instances sharded contiguously over the ranks, NO data-path collective, and ONE exchange at the end that lands every
+rank's packed results on rank `dst` (where the caller -- the agent loop -- lives).
+
+Transports of that one exchange (`ShardedMPC(transport=...)`, "auto" tries them in this order):
+
+  "peer"  the control / speed kernels of rank r store their outputs STRAIGHT INTO rank dst's slab over NVLink: the
+          output pointers handed to acmpc_solve_batch_device are peer-mapped views of dst's buffer (symmetric memory:
+          CUDA VMM handles exchanged once at start-up).  9.8 MB per rank and step at 4096 instances = 16 GB/s per rank,
+          nothing for NVLink 5, and no copy engine, no NCCL CTAs competing with the persistent control kernel for SMs.
+          What remains per step is a completion signal (a one-element NCCL all-reduce on a side stream).
+  "nccl"  every rank solves into its own HBM, then ONE NCCL gather of the packed buffers to dst (grouped send/recv
+          over NVLink).  The round-1 path; also what the CPU tests run over gloo.
+
+Steps are triple-buffered: the exchange / completion signal of step i runs on a side stream while the kernels of step
+i + 1 run.  The kernels of step i wait for the exchange of step i - 2 only (never for the one still in flight), and that
+is what makes the buffer they write -- last used by step i - 3 -- safe: dst joins the exchange of step i - 2 after it
+has consumed the results of step i - 3 (contract of wait(): the views are valid until dst's NEXT submit).
+
+    sh = ShardedMPC(cfg, fields=[...])                       # after dist.init_process_group
+    out = sh.solve(paths, offsets, vmax, is_localised)       # HOST global batch in (every rank passes the same arrays,
+                                                             # or only its own shard with local=True);
+                                                             # dict of numpy arrays for the WHOLE batch on dst, None elsewhere
+    t = sh.submit_device(d_paths, d_offsets, d_vmax, loc)    # device-resident shard, asynchronous
+    views = sh.wait(t)                                       # dst: dict name -> list of per-rank CUDA views (instance order),
+                                                             # valid until the next submit
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _capi
+from .sharding import packed_layout, shard_range
+
+
+NBUF = 3
+
+
+class _Ticket:
+    __slots__ = ("buf", "sizes", "B_total", "step")
+
+    def __init__(self, buf, sizes, B_total, step):
+        self.buf, self.sizes, self.B_total, self.step = buf, sizes, B_total, step
+
+
+class ShardedMPC:
+    def __init__(self, cfg: "_capi.Config", fields=None, group=None, dst: int = 0, device: Optional[int] = None,
+                 transport: str = "auto", solver=None):
+        import torch
+        import torch.distributed as dist
+
+        self._torch, self._dist = torch, dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dst = int(dst)
+        self.H = int(cfg.horizon)
+        spec = _capi.output_spec(self.H)
+        self.fields = list(spec) if fields is None else list(fields)
+        if solver is None:
+            from .solver import BatchedMPC
+
+            solver = BatchedMPC(cfg, torch.cuda.current_device() if device is None else device)
+        self.solver = solver
+        self.cuda = bool(getattr(solver, "device", None) is not None and torch.cuda.is_available())
+        self.device = torch.device("cuda", solver.device) if self.cuda else torch.device("cpu")
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be auto | peer | nccl")
+        self._want = transport
+        self.transport = None            # decided at the first allocation
+        self.transport_note = ""
+        self._cap_B = 0                  # instances per rank the buffers hold
+        self._cap = 0                    # bytes per slab
+        self._step = 0
+        self._side = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self._signal = None
+        self._sig_done = [None] * NBUF
+        self._local = [None] * NBUF      # packed output buffer of this rank (a view into dst's slab for "peer")
+        self._gathered = [None] * NBUF   # dst: world * cap bytes
+        self._symm = None
+        self._host_in = None
+        self._host_out = None
+        self._host_sizes = None
+
+    # -- buffers --------------------------------------------------------------------------------------------------
+    def _ensure(self, B_cap: int):
+        """(Re)allocate for shards of up to B_cap instances.  Collective: every rank calls it with the same value."""
+        torch, dist = self._torch, self._dist
+        if B_cap <= self._cap_B:
+            return
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
+        self._cap_B = int(B_cap)
+        self._sig_done = [None] * NBUF
+        self._step = 0
+        self._cap = packed_layout(self._cap_B, self.H, self.fields)[1]
+        total = self.world * self._cap
+        self.transport = None
+        if self.world == 1:
+            self.transport = "local"
+            for b in range(NBUF):
+                self._gathered[b] = torch.empty(total, dtype=torch.uint8, device=self.device)
+                self._local[b] = self._gathered[b]
+            return
+        if self.cuda and self._want in ("auto", "peer"):
+            try:
+                self._alloc_peer(total)
+                self.transport = "peer"
+            except Exception as e:      # noqa: BLE001 -- any failure of the VMM / handle exchange means: use NCCL
+                self.transport_note = f"peer transport unavailable ({type(e).__name__}: {e})"
+                if self._want == "peer":
+                    raise
+            # every rank must have made the same choice
+            ok = torch.tensor([1 if self.transport == "peer" else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                self.transport = None
+        if self.transport is None:
+            self.transport = "nccl"
+            for b in range(NBUF):
+                self._local[b] = torch.empty(self._cap, dtype=torch.uint8, device=self.device)
+                self._gathered[b] = (torch.empty(total, dtype=torch.uint8, device=self.device)
+                                     if self.rank == self.dst else None)
+        if self.cuda:
+            self._signal = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _alloc_peer(self, total: int):
+        """Symmetric memory: every rank allocates NBUF x total bytes, the handles are exchanged once, and rank r's output
+        buffer becomes the view [r * cap, (r + 1) * cap) of DST's allocation, mapped into r's address space."""
+        torch, dist = self._torch, self._dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        grp = self.group if self.group is not None else dist.group.WORLD
+        t = symm_mem.empty(NBUF * total, dtype=torch.uint8, device=self.device)
+        hdl = symm_mem.rendezvous(t, grp)
+        self._symm = (t, hdl)
+        mine = t if self.rank == self.dst else hdl.get_buffer(self.dst, (NBUF * total,), torch.uint8)
+        for b in range(NBUF):
+            whole = mine[b * total:(b + 1) * total]
+            self._gathered[b] = whole if self.rank == self.dst else None
+            self._local[b] = whole[self.rank * self._cap:(self.rank + 1) * self._cap]
+
+    def _views(self, packed, B: int):
+        from .solver import BatchedMPC
+
+        return BatchedMPC.unpack(packed, B, self.H, self.fields)
+
+    # -- device-resident shard ------------------------------------------------------------------------------------
+    def submit_device(self, d_paths, d_offsets=None, d_vmax=None, is_localised: bool = False, B_total: Optional[int] = None,
+                      warm=None, warm_valid: bool = True) -> _Ticket:
+        """Solve this rank's shard (device tensors) and start the exchange; asynchronous.  Every rank calls it."""
+        torch, dist = self._torch, self._dist
+        B = int(d_paths.shape[0])
+        if B_total is None:
+            B_total = B * self.world
+        sizes = [shard_range(B_total, r, self.world) for r in range(self.world)]
+        lo, hi = sizes[self.rank]
+        if hi - lo != B:
+            raise ValueError(f"rank {self.rank} holds {B} instances, shard_range says {hi - lo}")
+        self._ensure(max(h - l for l, h in sizes))
+        buf = self._step % NBUF
+        main = torch.cuda.current_stream(self.device) if self.cuda else None
+        prev2 = self._sig_done[(self._step - 2) % NBUF] if self._step >= 2 else None
+        if self.cuda and prev2 is not None:
+            # buffer `buf` was last used by step - 3; the exchange of step - 2 (which dst joined only after consuming
+            # step - 3, and which has overlapped the kernels of step - 1) must be complete before it is overwritten
+            main.wait_event(prev2)
+        views = self._views(self._local[buf][: packed_layout(B, self.H, self.fields)[1]], B)
+        self.solver.solve_device(d_paths, d_offsets, d_vmax, is_localised, out=views, warm=warm, warm_valid=warm_valid)
+        if self.world > 1:
+            if self.cuda:
+                solved = torch.cuda.Event()
+                solved.record(main)
+                self._side.wait_event(solved)
+                with torch.cuda.stream(self._side):
+                    self._exchange(buf)
+                    done = torch.cuda.Event()
+                    done.record(self._side)
+                self._sig_done[buf] = done
+            else:
+                self._exchange(buf)
+        self._step += 1
+        return _Ticket(buf, sizes, B_total, self._step - 1)
+
+    def _exchange(self, buf: int):
+        dist = self._dist
+        if self.transport == "peer":
+            dist.all_reduce(self._signal, group=self.group)          # completion signal only: the data is already there
+        else:
+            slots = list(self._gathered[buf].view(self.world, -1).unbind(0)) if self.rank == self.dst else None
+            dist.gather(self._local[buf], slots, dst=self.dst, group=self.group)
+
+    def wait(self, ticket: _Ticket, stream=None):
+        """Make `stream` (default: the current stream) wait for the exchange of `ticket`.  dst: dict name -> list of
+        per-rank views of the gathered results (instance order); other ranks: None.  The views stay valid until the
+        next-but-one submit."""
+        torch = self._torch
+        if self.cuda and self.world > 1:
+            s = torch.cuda.current_stream(self.device) if stream is None else stream
+            s.wait_event(self._sig_done[ticket.buf])
+        if self.rank != self.dst:
+            return None
+        whole = self._gathered[ticket.buf]
+        out: Dict[str, List] = {k: [] for k in self.fields}
+        for r, (lo, hi) in enumerate(ticket.sizes):
+            v = self._views(whole[r * self._cap:(r + 1) * self._cap], hi - lo)
+            for k in self.fields:
+                out[k].append(v[k])
+        return out
+
+    def drain(self):
+        """Block the host until every submitted step and its exchange are complete."""
+        if self.cuda:
+            self._torch.cuda.synchronize(self.device)
+
+    # -- host global batch (the call a user makes) ------------------------------------------------------------------
+    def solve(self, paths, offsets=None, vmax=None, is_localised: bool = False, local: bool = False,
+              B_total: Optional[int] = None) -> Optional[Dict[str, np.ndarray]]:
+        """HOST arrays in, HOST arrays out on dst.  `local=False`: every rank passes the same GLOBAL arrays and takes its
+        own shard_range slice; `local=True`: each rank passes only its shard (then B_total = sum over ranks is required
+        unless all shards are equal).  Pinned staging buffers are kept between calls; synchronous."""
+        torch = self._torch
+        paths = np.asarray(paths, dtype=np.float64)
+        if local:
+            B = paths.shape[0]
+            if B_total is None:
+                B_total = B * self.world
+            lo, hi = shard_range(B_total, self.rank, self.world)
+            if hi - lo != B:
+                raise ValueError("local shard size does not match shard_range(B_total, rank, world)")
+            sl = slice(0, B)
+        else:
+            B_total = paths.shape[0]
+            lo, hi = shard_range(B_total, self.rank, self.world)
+            B, sl = hi - lo, slice(lo, hi)
+        H = self.H
+        pin = self.cuda
+        if self._host_in is None or self._host_in[0].shape[0] < B:
+            mk = lambda *shape: (torch.empty(shape, dtype=torch.float64).pin_memory() if pin
+                                 else torch.empty(shape, dtype=torch.float64))
+            self._host_in = (mk(B, H, 3), mk(B), mk(B))
+            self._dev_in = tuple(torch.empty_like(t, device=self.device) for t in self._host_in)
+        hp, ho, hv = (t[:B] for t in self._host_in)
+        dp, do, dv = (t[:B] for t in self._dev_in)
+        hp.numpy()[...] = paths[sl]
+        dp.copy_(hp, non_blocking=True)
+        if offsets is not None:
+            ho.numpy()[...] = np.asarray(offsets, dtype=np.float64)[sl]
+            do.copy_(ho, non_blocking=True)
+        if vmax is not None:
+            hv.numpy()[...] = np.asarray(vmax, dtype=np.float64)[sl]
+            dv.copy_(hv, non_blocking=True)
+        t = self.submit_device(dp, do if offsets is not None else None, dv if vmax is not None else None, is_localised,
+                               B_total=B_total)
+        views = self.wait(t)
+        if self.rank != self.dst:
+            self.drain()
+            return None
+        # one D2H of the whole gathered buffer into pinned memory, then typed numpy views (instance order)
+        whole = self._gathered[t.buf]
+        if self._host_out is None or self._host_out.numel() < whole.numel():
+            self._host_out = torch.empty(whole.numel(), dtype=torch.uint8)
+            if pin:
+                self._host_out = self._host_out.pin_memory()
+        h = self._host_out[: whole.numel()]
+        h.copy_(whole, non_blocking=True)
+        self.drain()
+        spec = _capi.output_spec(H)
+        out = {}
+        hn = h.numpy()
+        for k in self.fields:
+            shp, dt = spec[k]
+            parts = []
+            for r, (l, u) in enumerate(t.sizes):
+                offs, _ = packed_layout(u - l, H, self.fields)
+                o, nb = offs[k]
+                parts.append(hn[r * self._cap + o: r * self._cap + o + nb].view(dt).reshape((u - l,) + shp))
+            out[k] = np.concatenate(parts, axis=0) if len(parts) > 1 else parts[0].copy()
+        del views
+        return out
