@@ -35,6 +35,7 @@ EXPORTED = [
     "acmpc_extract_paths_device", "acmpc_extract_paths_host",
     "acmpc_speed_profile_batch_device", "acmpc_speed_profile_batch_host", "acmpc_t2s_host", "acmpc_s2t_host",
     "acmpc_linearise_host", "acmpc_remove_near_duplicates_cols_host",
+    "acmpc_attach_completion", "acmpc_stream_wait_value32",
 ]
 
 RC_NAMES = {0: "ACMPC_OK", 1: "ACMPC_ERR_INVALID", 2: "ACMPC_ERR_CUDA", 3: "ACMPC_ERR_NO_DEVICE"}
@@ -197,6 +198,10 @@ def load() -> C.CDLL:
     L.acmpc_linearise_host.restype = C.c_int32
     L.acmpc_remove_near_duplicates_cols_host.argtypes = [vp, C.c_int32, C.c_int32, dp, C.c_double, dp, ip]
     L.acmpc_remove_near_duplicates_cols_host.restype = C.c_int32
+    L.acmpc_attach_completion.argtypes = [vp, vp, C.c_uint32, vp, C.c_int32, C.c_uint32, vp, C.c_uint32]
+    L.acmpc_attach_completion.restype = C.c_int32
+    L.acmpc_stream_wait_value32.argtypes = [vp, vp, C.c_uint32, vp]
+    L.acmpc_stream_wait_value32.restype = C.c_int32
     _lib = L
     return L
 

@@ -58,6 +58,22 @@ struct KernelParams {
     // Two counter sets alternate between launches: the control kernel zeroes the set of the NEXT launch.
     int32_t* order;
     int32_t order_set;
+    // Multi-GPU completion protocol (ShardedMPC, transport "peer"): the outputs of this launch may live in ANOTHER GPU's
+    // memory (peer-mapped over NVLink).  `flag` (in the consumer's memory) receives `flag_value` once every store of
+    // both kernels is visible system-wide: the last CTA of the control kernel to finish (counted in `done`) writes it.
+    // `credit_table[0..credit_n)` = addresses of the producers' credit words, written with `credit_value` when the speed
+    // kernel starts (the consumer's own launch hands back the buffers it has finished reading).
+    uint32_t* done;
+    uint32_t* flag;
+    uint32_t flag_value;
+    uint32_t credit_value;
+    const unsigned long long* credit_table;
+    int32_t credit_n;
+    // producer side of the credits: no CTA of the speed kernel starts before *credit_wait >= credit_need (a LOCAL word
+    // the consumer's launch writes remotely) -- the buffers this launch stores into are free from then on.  Polled in
+    // the kernel rather than with a stream wait op, so back-to-back launches stay pipelined.
+    const uint32_t* credit_wait;
+    uint32_t credit_need;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -194,6 +210,21 @@ __global__ void __launch_bounds__(32, OCC) acmpc_speed_kernel(const __grid_const
     // slowest warp is done
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
+    if (p.credit_n > 0 && blockIdx.x == 0 && lane < p.credit_n) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(p.credit_table[lane]);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(w), "r"(p.credit_value) : "memory");
+    }
+    if (p.credit_wait) {
+        if (lane == 0) {
+            uint32_t v;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.credit_wait) : "memory");
+                if (v >= p.credit_need) break;
+                __nanosleep(200);
+            }
+        }
+        __syncwarp();
+    }
     int32_t* cnt = p.order ? p.order + 8 * p.order_set : nullptr;
     const int b = (p.order && p.vmax) ? ordered_instance(cnt, p.order + 16, p.B, blockIdx.x) : (int)blockIdx.x;
     const int H = p.cfg.horizon, n = H - 1;
@@ -265,9 +296,19 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C == 2 ? 2 :
         item = next < (uint32_t)p.B ? (int)next : p.B;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (p.flag) __threadfence_system();   // this thread's output stores (possibly to a peer GPU) before the CTA signs off
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
+    if (p.flag && threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned prev = atomicAdd(p.done, 1u);
+        if (prev == gridDim.x - 1) {      // last CTA of the launch: everybody's stores are ordered before this point
+            *p.done = 0;                  // the next launch on this slot starts from zero (stream-ordered)
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag), "r"(p.flag_value) : "memory");
+        }
+    }
 }
 
 // FP64 FMA throughput probe: 8 independent chains per thread, no memory traffic.
@@ -315,6 +356,14 @@ struct acmpc_handle {
     int profiling;           // record events around the two kernels (acmpc_set_profiling)
     cudaEvent_t* ev;         // 3 * kEventRing events
     int ev_head, ev_count;
+    uint32_t* d_done;        // "CTAs finished" counters of the completion protocol, one per slot
+    // one-shot attachment for the next device-entry launch (acmpc_attach_completion)
+    uint32_t* att_flag;
+    uint32_t att_flag_value, att_credit_value;
+    const unsigned long long* att_credit_table;
+    int att_credit_n;
+    const uint32_t* att_credit_wait;
+    uint32_t att_credit_need;
     int persistent;          // persistent control-kernel warps + work queue (ACMPC_PERSISTENT=0 switches it off)
     int last_launches, last_smem, last_threads, last_ipc;
 };
@@ -457,6 +506,12 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     p.persistent = h->persistent;
     if (p.persistent && ctas > resident) ctas = resident;
     p.queue = h->d_queue + qi, p.queue_base = h->queue_pos[qi], p.warps_launched = (uint32_t)(ctas * kWarpsPerCta);
+    if (qi == kDeviceSlot && (h->att_flag || h->att_credit_n > 0 || h->att_credit_wait)) {   // consumed by this launch
+        p.done = h->d_done + qi, p.flag = h->att_flag, p.flag_value = h->att_flag_value;
+        p.credit_table = h->att_credit_table, p.credit_n = h->att_credit_n, p.credit_value = h->att_credit_value;
+        p.credit_wait = h->att_credit_wait, p.credit_need = h->att_credit_need;
+        h->att_flag = nullptr, h->att_credit_table = nullptr, h->att_credit_n = 0, h->att_credit_wait = nullptr;
+    }
     // longest-first order for batches that run several rounds of the device (see KernelParams::order)
     p.order = nullptr;
     if (h->order_on && B >= h->order_min && h->d_order[qi] && (size_t)B <= h->order_cap[qi]) {
@@ -660,7 +715,9 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
         return ACMPC_ERR_NO_DEVICE;
     }
     h->sm_count = prop.multiProcessorCount;
-    h->d_queue = nullptr;
+    h->d_queue = nullptr, h->d_done = nullptr;
+    h->att_flag = nullptr, h->att_credit_table = nullptr, h->att_credit_n = 0, h->att_flag_value = h->att_credit_value = 0;
+    h->att_credit_wait = nullptr, h->att_credit_need = 0;
     for (int k = 0; k < 4; ++k) h->streams[k] = nullptr;
     for (int k = 0; k < kSlots; ++k) h->queue_pos[k] = 0;
     h->d_vel = nullptr, h->vel_bytes = 0;
@@ -693,11 +750,14 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
              "cudaFuncSetAttribute(carveout)") ||
         fail(h, cudaMalloc(&h->d_queue, kSlots * sizeof(uint32_t)), "cudaMalloc(queue)") ||
         fail(h, cudaMemset(h->d_queue, 0, kSlots * sizeof(uint32_t)), "cudaMemset(queue)") ||
+        fail(h, cudaMalloc(&h->d_done, kSlots * sizeof(uint32_t)), "cudaMalloc(done)") ||
+        fail(h, cudaMemset(h->d_done, 0, kSlots * sizeof(uint32_t)), "cudaMemset(done)") ||
         fail(h, cudaStreamCreateWithFlags(&h->streams[0], cudaStreamNonBlocking), "cudaStreamCreate") ||
         fail(h, cudaStreamCreateWithFlags(&h->streams[1], cudaStreamNonBlocking), "cudaStreamCreate") ||
         fail(h, cudaStreamCreateWithFlags(&h->streams[2], cudaStreamNonBlocking), "cudaStreamCreate") ||
         fail(h, cudaStreamCreateWithFlags(&h->streams[3], cudaStreamNonBlocking), "cudaStreamCreate")) {
         if (h->d_queue) cudaFree(h->d_queue);
+        if (h->d_done) cudaFree(h->d_done);
         delete h;
         return ACMPC_ERR_CUDA;
     }
@@ -732,6 +792,7 @@ int32_t acmpc_destroy(acmpc_handle* h)
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->d_queue) cudaFree(h->d_queue);
+    if (h->d_done) cudaFree(h->d_done);
     if (h->d_vel) cudaFree(h->d_vel);
     if (h->d_warm) cudaFree(h->d_warm);
     for (int k = 0; k < kSlots; ++k)
@@ -976,6 +1037,44 @@ int32_t acmpc_speed_profile_batch_host(acmpc_handle* h, int32_t B, double* waypo
             if (rho_updates) rho_updates[b] = ru2[2 * b];
         }
     return rc;
+}
+
+int32_t acmpc_attach_completion(acmpc_handle* h, uint32_t* d_flag, uint32_t flag_value, const uint64_t* d_credit_table,
+                                int32_t credit_n, uint32_t credit_value, const uint32_t* d_credit_wait, uint32_t credit_need)
+{
+    if (!h || credit_n < 0 || credit_n > 32 || (credit_n > 0 && !d_credit_table)) return ACMPC_ERR_INVALID;
+    h->att_credit_wait = d_credit_wait, h->att_credit_need = credit_need;
+    h->att_flag = d_flag, h->att_flag_value = flag_value;
+    h->att_credit_table = reinterpret_cast<const unsigned long long*>(d_credit_table), h->att_credit_n = credit_n;
+    h->att_credit_value = credit_value;
+    return ACMPC_OK;
+}
+
+int32_t acmpc_stream_wait_value32(acmpc_handle* h, const uint32_t* d_addr, uint32_t value, void* stream)
+{
+    if (!h || !d_addr || (reinterpret_cast<uintptr_t>(d_addr) & 3)) return ACMPC_ERR_INVALID;
+    if (fail(h, cudaSetDevice(h->device), "cudaSetDevice")) return ACMPC_ERR_CUDA;
+    // cuStreamWaitValue32 (driver API) through the runtime's entry-point query: the library does not link libcuda, so it
+    // still loads on a box without a driver (the CPU-side tests)
+    typedef int (*wait_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+    static wait_fn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (fail(h, cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &st), "cudaGetDriverEntryPoint") ||
+            st != cudaDriverEntryPointSuccess || !f) {
+            h->err = "cuStreamWaitValue32 is not available from this driver";
+            return ACMPC_ERR_CUDA;
+        }
+        fn = reinterpret_cast<wait_fn>(f);
+    }
+    const int rc = fn(static_cast<cudaStream_t>(stream), (unsigned long long)reinterpret_cast<uintptr_t>(d_addr), value,
+                      0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (rc != 0) {
+        h->err = "cuStreamWaitValue32 failed with CUresult " + std::to_string(rc);
+        return ACMPC_ERR_CUDA;
+    }
+    return ACMPC_OK;
 }
 
 int32_t acmpc_last_launch_info(const acmpc_handle* h, int32_t* n_launches, int32_t* smem_bytes,

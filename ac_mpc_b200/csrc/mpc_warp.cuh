@@ -1643,27 +1643,31 @@ AC_DEV int speed_instance(const Ctx<C>& c, const double* raw_path, double v_max_
     SpeedQP<C> sq(c);
     sq.assemble_and_scale(path, v_max_live, localised);
     sq.solve(si, vel, warm, localised ? 1 : 0, use_warm);
-    AC_UNROLL
-    for (int j = 0; j < C; ++j) {
-        VI st = c.stage(j);
-        VB ok = vi_lt(st, n);
-        if (way) {
-            if (si.status == ACMPC_SOLVED) st_idx_if(ok, way + 6 * n, st, vel[j]);
-            if (vel_out) st_idx_if(ok, vel_out, st, vel[j]);
-            continue;
-        }
-        vel[j] = (si.status == ACMPC_SOLVED) ? vsel(ok, vel[j], VD(0.0)) : VD(0.0);
-        st_idx_if(ok, vel_out, st, vel[j]);
+    // Outputs leave as coalesced rows: lane l owns stages C*l .., a stride-C pattern that would write half-empty
+    // sectors (and, when the outputs are peer-mapped, one small NVLink write each); every row goes through a
+    // shared-memory tile and is written out lane-contiguous.  The scratch region is dead after the solve.
+    double* T = c.W;
+    auto row = [&](double* dst, const VD (&v)[C]) {
+        warp_sync();
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) st_idx_if(vi_lt(c.stage(j), n), T, c.stage(j), v[j]);
+        warp_sync();
+        warp_copy(dst, T, n);
+    };
+    if (way) {
+        if (si.status == ACMPC_SOLVED) row(way + 6 * n, vel);
+        if (vel_out) row(vel_out, vel);
+    } else {
+        AC_UNROLL
+        for (int j = 0; j < C; ++j)
+            vel[j] = (si.status == ACMPC_SOLVED) ? vsel(vi_lt(c.stage(j), n), vel[j], VD(0.0)) : VD(0.0);
+        row(vel_out, vel);
         if (o.waypoints) {
-            st_idx_if(ok, o.waypoints + 0 * n, st, path.xs[j]);
-            st_idx_if(ok, o.waypoints + 1 * n, st, path.ys[j]);
-            st_idx_if(ok, o.waypoints + 2 * n, st, path.psi[j]);
-            st_idx_if(ok, o.waypoints + 3 * n, st, path.kap[j]);
-            st_idx_if(ok, o.waypoints + 4 * n, st, path.dist[j]);
-            st_idx_if(ok, o.waypoints + 5 * n, st, path.wid[j]);
-            st_idx_if(ok, o.waypoints + 6 * n, st, vel[j]);
+            row(o.waypoints + 0 * n, path.xs), row(o.waypoints + 1 * n, path.ys), row(o.waypoints + 2 * n, path.psi);
+            row(o.waypoints + 3 * n, path.kap), row(o.waypoints + 4 * n, path.dist), row(o.waypoints + 5 * n, path.wid);
+            row(o.waypoints + 6 * n, vel);
         }
-        if (o.v_ref && o.v_ref != vel_out) st_idx_if(ok, o.v_ref, st, vel[j]);
+        if (o.v_ref && o.v_ref != vel_out) row(o.v_ref, vel);
     }
     AC_LANE0
     {
@@ -1696,46 +1700,77 @@ AC_DEV void control_instance(const Ctx<C>& c, const double* raw_path, const doub
     cq.solve(ci, warm, use_warm);
     // unpack (spatial_mpc.py:193-212) and roll out (dynamics.py:42-63)
     const double L = c.cfg->wheelbase;
-    VD un[C][3];
+    VD un[C][3], uv[C], uk[C];
     AC_UNROLL
     for (int j = 0; j < C; ++j) {
-        VI st = c.stage(j);
-        VB isx = vi_lt(st, H), ok = vi_lt(st, n), hasU = vi_ge(st, 1) & isx;
-        VD ey = cq.x[j][0] / c.ld(K_DI + 0, j);
-        VD ep = cq.x[j][1] / c.ld(K_DI + 1, j);
-        VD tt = cq.x[j][2] / c.ld(K_DI + 2, j);
-        VD v = cq.x[j][3] / c.ld(K_DI + 3, j);
-        VD kc = cq.x[j][4] / c.ld(K_DI + 4, j);
-        if (o.states) {
-            st_idx_if(isx, o.states, st * 3, ey);
-            st_idx_if(isx, o.states, st * 3 + 1, ep);
-            st_idx_if(isx, o.states, st * 3 + 2, tt);
+        un[j][0] = cq.x[j][0] / c.ld(K_DI + 0, j);                  // e_y
+        un[j][1] = cq.x[j][1] / c.ld(K_DI + 1, j);                  // e_psi
+        un[j][2] = cq.x[j][2] / c.ld(K_DI + 2, j);                  // t
+        uv[j] = cq.x[j][3] / c.ld(K_DI + 3, j);                     // v        (u_{s-1} lives with stage s)
+        uk[j] = vatan((cq.x[j][4] / c.ld(K_DI + 4, j)) * VD(L));    // delta = atan(kappa_cmd L)
+    }
+    // every output array leaves as coalesced rows through a shared-memory tile (see speed_instance); the scan region
+    // is dead after the solve
+    double* T = c.W;
+    if (o.states) {
+        warp_sync();
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VI st = c.stage(j);
+            VB isx = vi_lt(st, H);
+            st_idx_if(isx, T, st * 3, un[j][0]), st_idx_if(isx, T, st * 3 + 1, un[j][1]), st_idx_if(isx, T, st * 3 + 2, un[j][2]);
         }
-        if (o.controls) {   // u_{s-1} lives with stage s
-            st_idx_if(hasU, o.controls, st + (-1), v);
-            st_idx_if(hasU, o.controls, st + (n - 1), vatan(kc * VD(L)));
+        warp_sync();
+        warp_copy(o.states, T, 3 * H);
+    }
+    if (o.controls) {
+        warp_sync();
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VI st = c.stage(j);
+            VB hasU = vi_ge(st, 1) & vi_lt(st, H);
+            st_idx_if(hasU, T, st + (-1), uv[j]), st_idx_if(hasU, T, st + (n - 1), uk[j]);
         }
-        if (o.prediction) {
+        warp_sync();
+        warp_copy(o.controls, T, 2 * n);
+    }
+    if (o.prediction) {
+        warp_sync();
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) {
+            VI st = c.stage(j);
+            VB ok = vi_lt(st, n);
             VD ps = c.ld(F_PSI, j);
-            st_idx_if(ok, o.prediction, st * 2, c.ld(F_XS, j) - ey * vsin(ps));
-            st_idx_if(ok, o.prediction, st * 2 + 1, c.ld(F_YS, j) + ey * vcos(ps));
+            st_idx_if(ok, T, st * 2, c.ld(F_XS, j) - un[j][0] * vsin(ps));
+            st_idx_if(ok, T, st * 2 + 1, c.ld(F_YS, j) + un[j][0] * vcos(ps));
         }
-        if (o.cum_time) st_idx_if(ok, o.cum_time, st, tt);
-        un[j][0] = ey, un[j][1] = ep, un[j][2] = tt;
+        warp_sync();
+        warp_copy(o.prediction, T, 2 * n);
+    }
+    if (o.cum_time) {
+        warp_sync();
+        AC_UNROLL
+        for (int j = 0; j < C; ++j) st_idx_if(vi_lt(c.stage(j), n), T, c.stage(j), un[j][2]);
+        warp_sync();
+        warp_copy(o.cum_time, T, n);
     }
     if (o.derived) {   // spatial_mpc.py:208-211 over x_0 .. x_{n-1}: times, accelerations (sic: e_y column), steer_rates
         VD nx[C][3];
         pull_next_k<C, 3>(un, nx);
+        warp_sync();
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
             VI st = c.stage(j);
             VB ok = vi_le(st, n - 2);
             VD dt = nx[j][2] - un[j][2];
-            st_idx_if(ok, o.derived, st, dt);
-            st_idx_if(ok, o.derived + (n - 1), st, (nx[j][0] - un[j][0]) / dt);
-            st_idx_if(ok, o.derived + 2 * (n - 1), st, (nx[j][1] - un[j][1]) / dt);
+            st_idx_if(ok, T, st, dt);
+            st_idx_if(ok, T, st + (n - 1), (nx[j][0] - un[j][0]) / dt);
+            st_idx_if(ok, T, st + 2 * (n - 1), (nx[j][1] - un[j][1]) / dt);
         }
+        warp_sync();
+        warp_copy(o.derived, T, 3 * (n - 1));
     }
+    warp_sync();   // the tile is the next instance's staging area
     AC_LANE0
     {
         if (o.cost) *o.cost = ci.obj_val;

@@ -319,6 +319,11 @@ AC_DEV VD tm_ld1(const Tm& t, int dcol)
     return r;
 }
 AC_DEV void warp_sync() {}
+// dst[0..count) = src[0..count), the warp's lanes taking consecutive elements (coalesced rows on the device)
+AC_DEV void warp_copy(double* dst, const double* src, int count)
+{
+    for (int i = 0; i < count; ++i) dst[i] = src[i];
+}
 
 }  // namespace acmpc
 
@@ -569,6 +574,10 @@ AC_DEV double tm_ld1(const Tm& t, int dcol)
     return o[0];
 }
 AC_DEV void warp_sync() { __syncwarp(); }
+AC_DEV void warp_copy(double* dst, const double* src, int count)
+{
+    for (int i = (int)(threadIdx.x & 31); i < count; i += 32) dst[i] = src[i];
+}
 
 }  // namespace acmpc
 #endif

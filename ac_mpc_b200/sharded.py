@@ -4,18 +4,23 @@ rank's packed results on rank `dst` (where the caller -- the agent loop -- lives
 
 Transports of that one exchange (`ShardedMPC(transport=...)`, "auto" tries them in this order):
 
-  "peer"  the control / speed kernels of rank r store their outputs STRAIGHT INTO rank dst's slab over NVLink: the
-          output pointers handed to acmpc_solve_batch_device are peer-mapped views of dst's buffer (symmetric memory:
-          CUDA VMM handles exchanged once at start-up).  9.8 MB per rank and step at 4096 instances = 16 GB/s per rank,
-          nothing for NVLink 5, and no copy engine, no NCCL CTAs competing with the persistent control kernel for SMs.
-          What remains per step is a completion signal (a one-element NCCL all-reduce on a side stream).
+  "peer"  compute + exchange in ONE kernel: the control / speed kernels of rank r store their outputs STRAIGHT INTO rank
+          dst's slab over NVLink -- the output pointers handed to acmpc_solve_batch_device are peer-mapped views of
+          dst's buffer (symmetric memory: CUDA VMM handles exchanged once at start-up).  9.8 MB per rank and step at 4096
+          instances = 16 GB/s per rank, nothing for NVLink 5.  No collective at all in steady state: the last CTA of the
+          control kernel writes a completion flag into dst's memory after a system-scope fence (acmpc_attach_completion),
+          dst's consumer stream waits on those flags with cuStreamWaitValue32 (no SM, no kernel -- an NCCL kernel could
+          not be scheduled reliably next to the persistent control kernel, which fills every SM's registers, shared and
+          tensor memory: measured at 8 GPUs, a per-step NCCL signal cost 0.3 ms of a 0.6 ms step), and dst's own
+          launch hands consumed buffers back by writing a credit word into every producer's memory.
   "nccl"  every rank solves into its own HBM, then ONE NCCL gather of the packed buffers to dst (grouped send/recv
           over NVLink).  The round-1 path; also what the CPU tests run over gloo.
 
-Steps are triple-buffered: the exchange / completion signal of step i runs on a side stream while the kernels of step
-i + 1 run.  The kernels of step i wait for the exchange of step i - 2 only (never for the one still in flight), and that
-is what makes the buffer they write -- last used by step i - 3 -- safe: dst joins the exchange of step i - 2 after it
-has consumed the results of step i - 3 (contract of wait(): the views are valid until dst's NEXT submit).
+Steps are triple-buffered.  "nccl": the gather of step i runs on a side stream while the kernels of step i + 1 run; the
+kernels of step i wait for the gather of step i - 2 only (never for the one still in flight).  "peer": the kernels of
+step i start only once a LOCAL credit word says dst has released step i - 3, the previous user of the buffer they
+write.  Contract of wait() in both: the views are valid until dst's NEXT submit -- whatever reads them must be ordered
+before that submit on dst's current stream.
 
     sh = ShardedMPC(cfg, fields=[...])                       # after dist.init_process_group
     out = sh.solve(paths, offsets, vmax, is_localised)       # HOST global batch in (every rank passes the same arrays,
@@ -83,6 +88,8 @@ class ShardedMPC:
         self._host_in = None
         self._host_out = None
         self._host_sizes = None
+        self._lv_cache, self._gv_cache, self._size_cache = {}, {}, {}
+        self._last_B = 0
 
     # -- buffers --------------------------------------------------------------------------------------------------
     def _ensure(self, B_cap: int):
@@ -93,6 +100,7 @@ class ShardedMPC:
         if self.cuda:
             torch.cuda.synchronize(self.device)
         self._cap_B = int(B_cap)
+        self._lv_cache, self._gv_cache, self._size_cache = {}, {}, {}
         self._sig_done = [None] * NBUF
         self._step = 0
         self._cap = packed_layout(self._cap_B, self.H, self.fields)[1]
@@ -133,19 +141,57 @@ class ShardedMPC:
         import torch.distributed._symmetric_memory as symm_mem
 
         grp = self.group if self.group is not None else dist.group.WORLD
-        t = symm_mem.empty(NBUF * total, dtype=torch.uint8, device=self.device)
+        # [ NBUF x world slabs | control: world flag words (128 B apart), then this rank's credit word ]
+        data = NBUF * total
+        ctrl = (self.world + 1) * 128
+        size = data + ctrl
+        t = symm_mem.empty(size, dtype=torch.uint8, device=self.device)
         hdl = symm_mem.rendezvous(t, grp)
+        t.zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)            # nobody signals before every control region is zero
         self._symm = (t, hdl)
-        mine = t if self.rank == self.dst else hdl.get_buffer(self.dst, (NBUF * total,), torch.uint8)
+        peers = [t if r == self.rank else hdl.get_buffer(r, (size,), torch.uint8) for r in range(self.world)]
+        self._peers = peers
+        mine = peers[self.dst]
         for b in range(NBUF):
             whole = mine[b * total:(b + 1) * total]
             self._gathered[b] = whole if self.rank == self.dst else None
             self._local[b] = whole[self.rank * self._cap:(self.rank + 1) * self._cap]
+        self._flag_addr = mine.data_ptr() + data + 128 * self.rank          # my completion flag, in dst's memory
+        self._flags_local = t.data_ptr() + data                              # dst: flag of rank r at + 128 r
+        self._credit_local = t.data_ptr() + data + 128 * self.world          # my credit word, in my memory
+        self._credit_table = None
+        if self.rank == self.dst:
+            addrs = [p.data_ptr() + data + 128 * self.world for p in peers]
+            self._credit_table = torch.tensor(addrs, dtype=torch.int64, device=self.device)
 
     def _views(self, packed, B: int):
         from .solver import BatchedMPC
 
         return BatchedMPC.unpack(packed, B, self.H, self.fields)
+
+    # typed views are built once per (buffer, shard size): a step must cost the host microseconds, not the ~0.4 ms that
+    # 8 ranks x 11 fields of tensor slicing take (measured: that alone capped 8 GPUs at 0.86 ms per step)
+    def _local_views(self, buf: int, B: int):
+        key = (buf, B)
+        v = self._lv_cache.get(key)
+        if v is None:
+            v = self._lv_cache[key] = self._views(self._local[buf][: packed_layout(B, self.H, self.fields)[1]], B)
+        return v
+
+    def _gathered_views(self, buf: int, sizes):
+        key = (buf, tuple(sizes))
+        out = self._gv_cache.get(key)
+        if out is None:
+            whole = self._gathered[buf]
+            out = {k: [] for k in self.fields}
+            for r, (lo, hi) in enumerate(sizes):
+                v = self._views(whole[r * self._cap:(r + 1) * self._cap], hi - lo)
+                for k in self.fields:
+                    out[k].append(v[k])
+            self._gv_cache[key] = out
+        return out
 
     # -- device-resident shard ------------------------------------------------------------------------------------
     def submit_device(self, d_paths, d_offsets=None, d_vmax=None, is_localised: bool = False, B_total: Optional[int] = None,
@@ -155,19 +201,35 @@ class ShardedMPC:
         B = int(d_paths.shape[0])
         if B_total is None:
             B_total = B * self.world
-        sizes = [shard_range(B_total, r, self.world) for r in range(self.world)]
+        sizes = self._size_cache.get(B_total)
+        if sizes is None:
+            sizes = [shard_range(B_total, r, self.world) for r in range(self.world)]
         lo, hi = sizes[self.rank]
         if hi - lo != B:
             raise ValueError(f"rank {self.rank} holds {B} instances, shard_range says {hi - lo}")
         self._ensure(max(h - l for l, h in sizes))
+        self._size_cache[B_total] = sizes
         buf = self._step % NBUF
         main = torch.cuda.current_stream(self.device) if self.cuda else None
-        prev2 = self._sig_done[(self._step - 2) % NBUF] if self._step >= 2 else None
+        prev2 = self._sig_done[(self._step - 2) % NBUF] if (self._step >= 2 and self.transport != "peer") else None
         if self.cuda and prev2 is not None:
             # buffer `buf` was last used by step - 3; the exchange of step - 2 (which dst joined only after consuming
             # step - 3, and which has overlapped the kernels of step - 1) must be complete before it is overwritten
             main.wait_event(prev2)
-        views = self._views(self._local[buf][: packed_layout(B, self.H, self.fields)[1]], B)
+        views = self._local_views(buf, B)
+        if self.transport == "peer":
+            step = self._step
+            # my kernels' last CTA raises my flag on dst to step + 1; dst's launch releases every step < `step`; buffer
+            # `buf` held step - NBUF, so my first kernel's CTAs start only once my (local) credit word says dst has
+            # released it (polled inside the kernel: no stream op between consecutive launches)
+            self.solver.attach_completion(self._flag_addr, step + 1,
+                                          self._credit_table.data_ptr() if self._credit_table is not None else 0,
+                                          self.world if self._credit_table is not None else 0, step,
+                                          self._credit_local if step >= NBUF else 0, max(step - NBUF + 1, 0))
+            self.solver.solve_device(d_paths, d_offsets, d_vmax, is_localised, out=views, warm=warm, warm_valid=warm_valid)
+            self._step += 1
+            self._last_B = B
+            return _Ticket(buf, sizes, B_total, step)
         self.solver.solve_device(d_paths, d_offsets, d_vmax, is_localised, out=views, warm=warm, warm_valid=warm_valid)
         if self.world > 1:
             if self.cuda:
@@ -182,33 +244,32 @@ class ShardedMPC:
             else:
                 self._exchange(buf)
         self._step += 1
+        self._last_B = B
         return _Ticket(buf, sizes, B_total, self._step - 1)
 
     def _exchange(self, buf: int):
-        dist = self._dist
-        if self.transport == "peer":
-            dist.all_reduce(self._signal, group=self.group)          # completion signal only: the data is already there
-        else:
-            slots = list(self._gathered[buf].view(self.world, -1).unbind(0)) if self.rank == self.dst else None
-            dist.gather(self._local[buf], slots, dst=self.dst, group=self.group)
+        slots = list(self._gathered[buf].view(self.world, -1).unbind(0)) if self.rank == self.dst else None
+        self._dist.gather(self._local[buf], slots, dst=self.dst, group=self.group)
 
     def wait(self, ticket: _Ticket, stream=None):
         """Make `stream` (default: the current stream) wait for the exchange of `ticket`.  dst: dict name -> list of
         per-rank views of the gathered results (instance order); other ranks: None.  The views stay valid until the
         next-but-one submit."""
         torch = self._torch
-        if self.cuda and self.world > 1:
+        if self.transport == "peer":
+            if self.rank == self.dst:      # every rank's completion flag for this step, stream-ordered, no SM involved
+                for r in range(self.world):
+                    self.solver.stream_wait_value32(self._flags_local + 128 * r, ticket.step + 1, stream)
+        elif self.cuda and self.world > 1:
             s = torch.cuda.current_stream(self.device) if stream is None else stream
             s.wait_event(self._sig_done[ticket.buf])
         if self.rank != self.dst:
             return None
-        whole = self._gathered[ticket.buf]
-        out: Dict[str, List] = {k: [] for k in self.fields}
-        for r, (lo, hi) in enumerate(ticket.sizes):
-            v = self._views(whole[r * self._cap:(r + 1) * self._cap], hi - lo)
-            for k in self.fields:
-                out[k].append(v[k])
-        return out
+        return self._gathered_views(ticket.buf, ticket.sizes)
+
+    def last_local_views(self):
+        """Typed views of what this rank's kernels wrote in the most recent step (its own slab)."""
+        return self._local_views((self._step - 1) % NBUF, self._last_B)
 
     def drain(self):
         """Block the host until every submitted step and its exchange are complete."""
@@ -242,41 +303,41 @@ class ShardedMPC:
                                  else torch.empty(shape, dtype=torch.float64))
             self._host_in = (mk(B, H, 3), mk(B), mk(B))
             self._dev_in = tuple(torch.empty_like(t, device=self.device) for t in self._host_in)
-        hp, ho, hv = (t[:B] for t in self._host_in)
+
+        def upload(dst_dev, stage, arr):
+            """H2D of arr[sl]: straight from the caller's buffer when it is pinned, through the pinned stage otherwise."""
+            src = torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=np.float64)[sl]))
+            if not (pin and src.is_pinned()):
+                stage.copy_(src)
+                src = stage
+            dst_dev.copy_(src, non_blocking=True)
+
         dp, do, dv = (t[:B] for t in self._dev_in)
-        hp.numpy()[...] = paths[sl]
-        dp.copy_(hp, non_blocking=True)
+        hp, ho, hv = (t[:B] for t in self._host_in)
+        upload(dp, hp, paths)
         if offsets is not None:
-            ho.numpy()[...] = np.asarray(offsets, dtype=np.float64)[sl]
-            do.copy_(ho, non_blocking=True)
+            upload(do, ho, offsets)
         if vmax is not None:
-            hv.numpy()[...] = np.asarray(vmax, dtype=np.float64)[sl]
-            dv.copy_(hv, non_blocking=True)
+            upload(dv, hv, vmax)
         t = self.submit_device(dp, do if offsets is not None else None, dv if vmax is not None else None, is_localised,
                                B_total=B_total)
         views = self.wait(t)
         if self.rank != self.dst:
             self.drain()
             return None
-        # one D2H of the whole gathered buffer into pinned memory, then typed numpy views (instance order)
-        whole = self._gathered[t.buf]
-        if self._host_out is None or self._host_out.numel() < whole.numel():
-            self._host_out = torch.empty(whole.numel(), dtype=torch.uint8)
-            if pin:
-                self._host_out = self._host_out.pin_memory()
-        h = self._host_out[: whole.numel()]
-        h.copy_(whole, non_blocking=True)
-        self.drain()
+        # D2H of every (rank, field) slab straight into its place in pinned whole-batch arrays (instance order): no host
+        # concatenation.  The returned arrays are views of those buffers, valid until the next solve() call.
         spec = _capi.output_spec(H)
-        out = {}
-        hn = h.numpy()
+        if self._host_out is None or self._host_out[0] != B_total:
+            bufs = {}
+            for k in self.fields:
+                shp, dt = spec[k]
+                h = torch.empty((B_total,) + shp, dtype=getattr(torch, dt))
+                bufs[k] = h.pin_memory() if pin else h
+            self._host_out = (B_total, bufs)
+        bufs = self._host_out[1]
         for k in self.fields:
-            shp, dt = spec[k]
-            parts = []
             for r, (l, u) in enumerate(t.sizes):
-                offs, _ = packed_layout(u - l, H, self.fields)
-                o, nb = offs[k]
-                parts.append(hn[r * self._cap + o: r * self._cap + o + nb].view(dt).reshape((u - l,) + shp))
-            out[k] = np.concatenate(parts, axis=0) if len(parts) > 1 else parts[0].copy()
-        del views
-        return out
+                bufs[k][l:u].copy_(views[k][r], non_blocking=True)
+        self.drain()
+        return {k: bufs[k].numpy() for k in self.fields}

@@ -487,6 +487,20 @@ class BatchedMPC:
 
         return torch.zeros(B * self.warm_stride() // 8, dtype=torch.float64, device=f"cuda:{self.device}")
 
+    def attach_completion(self, flag_ptr: int = 0, flag_value: int = 0, credit_table_ptr: int = 0, credit_n: int = 0,
+                          credit_value: int = 0, credit_wait_ptr: int = 0, credit_need: int = 0):
+        """One-shot for the next solve_device (acmpc_attach_completion): raw device addresses, see include/acmpc_b200.h."""
+        self._check(self._lib.acmpc_attach_completion(self._handle(), C.c_void_p(flag_ptr or None), int(flag_value),
+                                                      C.c_void_p(credit_table_ptr or None), int(credit_n), int(credit_value),
+                                                      C.c_void_p(credit_wait_ptr or None), int(credit_need)))
+
+    def stream_wait_value32(self, addr: int, value: int, stream=None):
+        """`stream` (torch stream, default: current) waits until the LOCAL device word at `addr` is >= value."""
+        import torch
+
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        self._check(self._lib.acmpc_stream_wait_value32(self._handle(), C.c_void_p(addr), int(value), C.c_void_p(s.cuda_stream)))
+
     def solve_device(self, paths, offsets=None, vmax=None, is_localised: bool = False, out=None, stream=None,
                      warm=None, warm_valid: bool = True):
         """DEVICE tensors in/out (acmpc_solve_batch_device); asynchronous on `stream` (torch stream or

@@ -138,6 +138,25 @@ int32_t acmpc_solve_batch_device(acmpc_handle *h, int32_t B, const double *d_pat
                                  int32_t is_localised, void *d_warm, int32_t warm_valid,
                                  const acmpc_outputs *d_out, void *stream);
 
+/* Multi-GPU completion protocol (ac_mpc_b200/sharded.py, transport "peer").  The output pointers
+ * of acmpc_solve_batch_device may be PEER-MAPPED: memory of another GPU of the node, so that the kernels store their
+ * results straight into the consumer's buffer over NVLink and no collective moves them afterwards.
+ *   acmpc_attach_completion  one-shot, applies to the NEXT acmpc_solve_batch_device call on this handle:
+ *       d_flag / flag_value     once every output store of that call is visible system-wide, the control kernel's last
+ *                               CTA writes flag_value to *d_flag (a word in the consumer's memory; may be NULL)
+ *       d_credit_table[credit_n] device array of addresses of the producers' credit words (<= 32); the call's first kernel
+ *                               writes credit_value to each: "the buffers of every step < credit_value are free again"
+ *       d_credit_wait / credit_need  producer side: no CTA of the call's first kernel starts before the LOCAL word
+ *                               *d_credit_wait is >= credit_need (polled inside the kernel, so consecutive launches
+ *                               stay pipelined; NULL = no wait)
+ *   acmpc_stream_wait_value32   makes `stream` wait until *d_addr >= value (cuStreamWaitValue32: no SM, no kernel);
+ *                               d_addr must be LOCAL device memory of the handle's GPU (the words above are written
+ *                               remotely, waited on locally). */
+int32_t acmpc_attach_completion(acmpc_handle *h, uint32_t *d_flag, uint32_t flag_value, const uint64_t *d_credit_table,
+                                int32_t credit_n, uint32_t credit_value, const uint32_t *d_credit_wait,
+                                uint32_t credit_need);
+int32_t acmpc_stream_wait_value32(acmpc_handle *h, const uint32_t *d_addr, uint32_t value, void *stream);
+
 /* Same with HOST buffers: copies inputs to the device, runs the kernels, copies every non-NULL
  * output back and synchronises.  keep_warm != 0: instance slot b of consecutive calls with the same B is one
  * persistent solver object (records live on the device inside the handle; a different B or a call with
