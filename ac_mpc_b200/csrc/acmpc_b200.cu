@@ -37,6 +37,7 @@ struct KernelParams {
     const double* vmax;
     double* vel;   // [B,n] speed profile: written by the speed kernel, read by the control kernel
     double* way;   // NULL, or [B,7,n] ReferencePath rows of the stand-alone speed profile (see speed_instance)
+    double* cold;  // split layout (C = 3): [launched warps, Layout<C>::kColdDoubles] cold per-stage fields in global memory
     double* warm;  // NULL or [B, Layout<C>::kWarmDoubles] warm-start records (read when use_warm, always rewritten)
     int32_t use_warm;
     acmpc_outputs out;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(32, OCC) acmpc_speed_kernel(const __grid_const
     const int b = (p.order && p.vmax) ? ordered_instance(cnt, p.order + 16, p.B, blockIdx.x) : (int)blockIdx.x;
     const int H = p.cfg.horizon, n = H - 1;
     acmpc::Ctx<C> c;
-    c.S = nullptr;
+    c.S = nullptr, c.HS = nullptr;
     c.W = reinterpret_cast<double*>(smem_raw);
     c.tm.a = 0;
     c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(32, OCC) acmpc_speed_kernel(const __grid_const
 
 // Kernel 2: control QP + unpack + rollout + cost.
 template <int C>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C == 2 ? 2 : 1)))
+__global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C <= 3 ? 2 : 1)))
     acmpc_control_kernel(const __grid_constant__ KernelParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -277,12 +278,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C == 2 ? 2 :
                               : item;
         const int H = p.cfg.horizon, n = H - 1;
         acmpc::Ctx<C> c;
-        c.S = reinterpret_cast<double*>(smem_raw + (size_t)warp * warp_smem_bytes<C>());
-        c.W = c.S + acmpc::K_FIELDS * C * 32;
+        using L = acmpc::Layout<C>;
+        double* base = reinterpret_cast<double*>(smem_raw + (size_t)warp * warp_smem_bytes<C>());
+        c.S = L::kColdGlobal ? p.cold + (size_t)(blockIdx.x * kWarpsPerCta + warp) * L::kColdDoubles : base;
+        c.W = L::kColdGlobal ? base : base + L::kColdDoubles;
+        c.HS = c.W + L::kScratch;
         c.tm.a = tmem_base + ((uint32_t)(32 * warp) << 16);
         c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
-        uint64_t* mbar = reinterpret_cast<uint64_t*>(c.S + acmpc::Layout<C>::kDoubles);
+        uint64_t* mbar = reinterpret_cast<uint64_t*>(base + L::kDoubles);
         // the raw path slice lands in the scratch region: it is dead before the first factorisation
+#ifdef ACMPC_PHASE_TIMING
+        c.tl = clock64();
+#endif
         stage_path(c.W, p.paths + (size_t)b * 3 * H, H, p.use_tma, mbar, lane);
         const double offset = p.offsets ? p.offsets[b] : 0.0;
         double* wrec = p.warm ? p.warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;
@@ -356,6 +363,8 @@ struct acmpc_handle {
     int profiling;           // record events around the two kernels (acmpc_set_profiling)
     cudaEvent_t* ev;         // 3 * kEventRing events
     int ev_head, ev_count;
+    double* d_cold;          // split layout: cold per-stage fields of every resident warp, one region per slot
+    size_t cold_stride;      // bytes per slot (0: this horizon keeps them in shared memory)
     uint32_t* d_done;        // "CTAs finished" counters of the completion protocol, one per slot
     // one-shot attachment for the next device-entry launch (acmpc_attach_completion)
     uint32_t* att_flag;
@@ -419,6 +428,14 @@ size_t warm_bytes_for(int H)
         case 2: return sizeof(double) * acmpc::Layout<2>::kWarmDoubles;
         case 3: return sizeof(double) * acmpc::Layout<3>::kWarmDoubles;
         default: return sizeof(double) * acmpc::Layout<4>::kWarmDoubles;
+    }
+}
+
+size_t cold_doubles_for(int H)   // per warp, 0 unless the horizon's layout keeps the cold fields in global memory
+{
+    switch (stages_per_lane(H)) {
+        case 3: return acmpc::Layout<3>::kColdGlobal ? acmpc::Layout<3>::kColdDoubles : 0;
+        default: return 0;
     }
 }
 
@@ -506,6 +523,7 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     p.persistent = h->persistent;
     if (p.persistent && ctas > resident) ctas = resident;
     p.queue = h->d_queue + qi, p.queue_base = h->queue_pos[qi], p.warps_launched = (uint32_t)(ctas * kWarpsPerCta);
+    p.cold = h->d_cold ? reinterpret_cast<double*>(reinterpret_cast<char*>(h->d_cold) + (size_t)qi * h->cold_stride) : nullptr;
     if (qi == kDeviceSlot && (h->att_flag || h->att_credit_n > 0 || h->att_credit_wait)) {   // consumed by this launch
         p.done = h->d_done + qi, p.flag = h->att_flag, p.flag_value = h->att_flag_value;
         p.credit_table = h->att_credit_table, p.credit_n = h->att_credit_n, p.credit_value = h->att_credit_value;
@@ -715,7 +733,7 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
         return ACMPC_ERR_NO_DEVICE;
     }
     h->sm_count = prop.multiProcessorCount;
-    h->d_queue = nullptr, h->d_done = nullptr;
+    h->d_queue = nullptr, h->d_done = nullptr, h->d_cold = nullptr, h->cold_stride = 0;
     h->att_flag = nullptr, h->att_credit_table = nullptr, h->att_credit_n = 0, h->att_flag_value = h->att_credit_value = 0;
     h->att_credit_wait = nullptr, h->att_credit_need = 0;
     for (int k = 0; k < 4; ++k) h->streams[k] = nullptr;
@@ -781,6 +799,17 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
         if (by_tmem < r) r = by_tmem;
         h->ctas_per_sm = r < 1 ? 1 : r;
     }
+    // split layout: the cold per-stage fields of every RESIDENT warp live in global memory (the kernel is persistent, so
+    // at most sm_count * ctas_per_sm CTAs are ever launched); one region per work-queue slot, launches of different
+    // slots may overlap
+    if (cold_doubles_for(cfg->horizon) > 0) {
+        h->cold_stride = (size_t)h->sm_count * h->ctas_per_sm * kWarpsPerCta * cold_doubles_for(cfg->horizon) * sizeof(double);
+        if (fail(h, cudaMalloc(&h->d_cold, kSlots * h->cold_stride), "cudaMalloc(cold fields)")) {
+            acmpc_destroy(h);
+            return ACMPC_ERR_CUDA;
+        }
+        h->persistent = 1;
+    }
     *out = h;
     return ACMPC_OK;
 }
@@ -793,6 +822,7 @@ int32_t acmpc_destroy(acmpc_handle* h)
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->d_queue) cudaFree(h->d_queue);
     if (h->d_done) cudaFree(h->d_done);
+    if (h->d_cold) cudaFree(h->d_cold);
     if (h->d_vel) cudaFree(h->d_vel);
     if (h->d_warm) cudaFree(h->d_warm);
     for (int k = 0; k < kSlots; ++k)
@@ -1076,6 +1106,16 @@ int32_t acmpc_stream_wait_value32(acmpc_handle* h, const uint32_t* d_addr, uint3
     }
     return ACMPC_OK;
 }
+
+#ifdef ACMPC_PHASE_TIMING
+// experiment builds only: read and reset the phase clocks of the control kernel
+extern "C" int32_t acmpc_exp_phase_cycles(unsigned long long* out16)
+{
+    if (cudaMemcpyFromSymbol(out16, acmpc::g_phase, 16 * sizeof(unsigned long long)) != cudaSuccess) return ACMPC_ERR_CUDA;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(acmpc::g_phase, z, sizeof(z)) == cudaSuccess ? ACMPC_OK : ACMPC_ERR_CUDA;
+}
+#endif
 
 int32_t acmpc_last_launch_info(const acmpc_handle* h, int32_t* n_launches, int32_t* smem_bytes,
                                int32_t* threads_per_cta, int32_t* instances_per_cta)

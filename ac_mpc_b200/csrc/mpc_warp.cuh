@@ -99,16 +99,35 @@ enum : int {
 template <int C>
 struct Layout {
     static constexpr int kWarmDoubles = WR_HEADER + (2 * WR_SPEED_FIELDS + WR_CTRL_FIELDS) * C * 32;
+    // C = 3 (horizons 65..96, e.g. the Spa H = 80 sweep): with the C = 2 recipe one instance needs 384 tensor-memory
+    // columns (-> a 512-column allocation: ONE CTA per SM) and 33 KB of shared memory.  The "split" layout brings it back
+    // to two CTAs = 8 instances per SM: the cold per-stage fields (read at termination checks, refactorisations and for
+    // the outputs only) live in a per-warp slice of GLOBAL memory (L2-resident), tensor memory keeps chunks F, G of all
+    // three stages and H of the first two (128 doubles per lane = 256 columns), and H of the third stage plus the three NS
+    // chunks sit in shared memory as lane-private columns next to the scan matrices, which drop their zero padding.
+    static constexpr bool kSplit = (C == 3);
+    static constexpr bool kColdGlobal = kSplit;
+    static constexpr int kColdDoubles = K_FIELDS * C * 32;          // cold per-stage fields of one instance
     // scan matrices: every element keeps 48 lanes; lanes 32..47 stay zero, so the backward scan reads
     // "lane + 2^L" without a bounds test and whatever its raw shuffle delivers there is cancelled
-    // (C = 1 keeps 32 lanes and the bounds test: the padding would cost it its third CTA per SM)
-    static constexpr int kScanLanes = (C == 1) ? 32 : 48;
+    // (C = 1 and the split layout keep 32 lanes and the bounds test: the padding would cost them a CTA per SM)
+    static constexpr int kScanLanes = (C == 1 || kSplit) ? 32 : 48;
     static constexpr int kScanDoubles = 9 * kLevels * kScanLanes;
     static constexpr int kScratch = (W_FIELDS * C * 32 > kScanDoubles) ? W_FIELDS * C * 32 : kScanDoubles;
-    static constexpr int kDoubles = K_FIELDS * C * 32 + kScratch;   // shared memory per warp, control phase
+    static constexpr int kHotSmemChunks = kSplit ? 4 : 0;           // 16-double chunks per lane kept in shared memory
+    static constexpr int kHotSmemDoubles = kHotSmemChunks * 16 * 32;
+    // shared memory per warp, control phase: [cold fields unless global | scratch / scan region | hot chunks]
+    static constexpr int kDoubles = (kColdGlobal ? 0 : kColdDoubles) + kScratch + kHotSmemDoubles;
     static constexpr int kSpeedDoubles = (2 * C * 32 > 3 * 32 * C) ? 2 * C * 32 : 3 * 32 * C;   // speed phase: raw path / LDL work
-    static constexpr int kTmemDoubles = T_STRIDE * C;               // tensor memory per lane
+    static constexpr int kTmemDoubles = kSplit ? 128 : T_STRIDE * C;   // tensor memory per lane
     static constexpr int kTmemCols = (2 * kTmemDoubles <= 128) ? 128 : ((2 * kTmemDoubles <= 256) ? 256 : 512);
+    // where chunk `ch` (T_F, T_G, T_H, T_NS) of the lane's stage j lives
+    AC_HD static constexpr bool in_smem(int ch, int j) { return kSplit && (ch == T_NS || (ch == T_H && j == 2)); }
+    AC_HD static constexpr int smem_slot(int ch, int j) { return ch == T_NS ? j : 3; }
+    AC_HD static constexpr int tmem_off(int ch, int j)
+    {
+        return !kSplit ? j * T_STRIDE + ch : (ch == T_H ? 96 + 16 * j : 32 * j + (ch == T_G ? 16 : 0));
+    }
 };
 template <int C>
 constexpr int smem_doubles()
@@ -250,10 +269,26 @@ AC_DEV bool dualgap_ok(const Norms& N, double cinv, double eps_abs, double eps_r
 // ------------------------------------------------------------------------------------------------
 // per-instance context
 // ------------------------------------------------------------------------------------------------
+// Phase clocks (instrumented experiment builds only, -DACMPC_PHASE_TIMING: tools/phase_timing.py): lane 0 adds the
+// cycles since the previous mark to g_phase[k].  Compiled out of the product.
+#if defined(ACMPC_PHASE_TIMING) && !defined(ACMPC_EMULATE)
+__device__ unsigned long long g_phase[16];
+#define AC_PHASE(c, k)                                                          \
+    do {                                                                        \
+        const long long t_ = clock64();                                         \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase[k], (unsigned long long)(t_ - (c).tl)); \
+        (c).tl = clock64();                                                     \
+    } while (0)
+#else
+#define AC_PHASE(c, k) ((void)0)
+#endif
+
 template <int C>
 struct Ctx {
-    double* S;   // this instance's (warp's) cold per-stage fields in shared memory (control phase only)
+    mutable long long tl;
+    double* S;   // this instance's (warp's) cold per-stage fields: shared memory, or global memory in the split layout
     double* W;   // this instance's scratch / scan region in shared memory
+    double* HS;  // split layout: the hot chunks kept in shared memory (lane-private columns)
     Tm tm;       // base of this instance's tensor-memory block (the warp's lane quarter; control phase only)
     int H, n;
     const acmpc_config* cfg;
@@ -266,9 +301,36 @@ struct Ctx {
     // element e of the level-L scan matrices: scan(L, e)[lane], lanes 0 .. 47
     AC_MEM double* scan(int lvl, int e) const { return scratch() + (lvl * 9 + e) * Layout<C>::kScanLanes; }
     AC_MEM VI stage(int j) const { return lane * C + j; }
-    // tensor-memory chunk `ch` (T_F, T_G, T_H, T_NS) of own stage j
-    AC_MEM void tld(int ch, int j, VD (&o)[16]) const { tm_ld<16>(tm, j * T_STRIDE + ch, o); }
-    AC_MEM void tst(int ch, int j, const VD (&v)[16]) const { tm_st<16>(tm, j * T_STRIDE + ch, v); }
+    // hot per-stage data: N doubles at offset `off` of chunk `ch` (T_F, T_G, T_H, T_NS) of own stage j -- from tensor
+    // memory or, for the chunks the split layout keeps there, from the lane's shared-memory column.  ch and j are
+    // compile-time constants at every call site (unrolled loops), so the routing folds away.
+    template <int N>
+    AC_MEM void hld(int ch, int off, int j, VD (&o)[N]) const
+    {
+        if (Layout<C>::in_smem(ch, j)) {
+            const double* p = HS + (Layout<C>::smem_slot(ch, j) * 16 + off) * 32;
+            AC_UNROLL
+            for (int k = 0; k < N; ++k) o[k] = ld_lane(p + k * 32);
+        } else {
+            tm_ld<N>(tm, Layout<C>::tmem_off(ch, j) + off, o);
+        }
+    }
+    AC_MEM VD hld1(int ch, int off, int j) const
+    {
+        if (Layout<C>::in_smem(ch, j)) return ld_lane(HS + (Layout<C>::smem_slot(ch, j) * 16 + off) * 32);
+        return tm_ld1(tm, Layout<C>::tmem_off(ch, j) + off);
+    }
+    AC_MEM void tld(int ch, int j, VD (&o)[16]) const { hld<16>(ch, 0, j, o); }
+    AC_MEM void tst(int ch, int j, const VD (&v)[16]) const
+    {
+        if (Layout<C>::in_smem(ch, j)) {
+            double* p = HS + Layout<C>::smem_slot(ch, j) * 16 * 32;
+            AC_UNROLL
+            for (int k = 0; k < 16; ++k) st_lane(p + k * 32, v[k]);
+        } else {
+            tm_st<16>(tm, Layout<C>::tmem_off(ch, j), v);
+        }
+    }
 };
 
 // value held by the NEXT stage (s+1) for every own stage; 0 beyond lane 31
@@ -1255,12 +1317,12 @@ struct ControlQP {
             VD F[9], G[16], Q[8];   // F: rho[5] iv ik rb31 rb22 (no rinv here); Q: q[2] be[3] lb[0..2]
             {
                 VD f8[8], f1[1];
-                tm_ld<8>(c.tm, j * T_STRIDE + T_F, f8), tm_ld<1>(c.tm, j * T_STRIDE + T_F + 8, f1);
+                c.template hld<8>(T_F, 0, j, f8), c.template hld<1>(T_F, 8, j, f1);
                 for (int k = 0; k < 8; ++k) F[k] = f8[k];
                 F[8] = f1[0];
             }
             c.tld(T_G, j, G);
-            tm_ld<8>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
+            c.template hld<8>(T_H, HC_Q, j, Q);
             const VD z0 = FIRST ? ze[j][0] : Q[HC_BE + 0], z1 = FIRST ? ze[j][1] : Q[HC_BE + 1],
                      z2 = FIRST ? ze[j][2] : Q[HC_BE + 2];
             VD w0 = VD(re) * z0 - ye[j][0], w1 = VD(re) * z1 - ye[j][1], w2 = VD(re) * z2 - ye[j][2];
@@ -1301,7 +1363,7 @@ struct ControlQP {
             {
                 VD g8[8], g2[2];
                 c.tld(T_F, j, F);
-                tm_ld<8>(c.tm, j * T_STRIDE + T_G, g8), tm_ld<2>(c.tm, j * T_STRIDE + T_G + 8, g2);
+                c.template hld<8>(T_G, 0, j, g8), c.template hld<2>(T_G, 8, j, g2);
                 c.tld(T_H, j, Hc);
                 for (int k = 0; k < 8; ++k) G[k] = g8[k];
                 G[8] = g2[0], G[9] = g2[1];
@@ -1383,11 +1445,11 @@ struct ControlQP {
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
             VD S5[8], Q[2];
-            tm_ld<8>(c.tm, j * T_STRIDE + T_G + GC_S, S5);
-            tm_ld<2>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
+            c.template hld<8>(T_G, GC_S, j, S5);
+            c.template hld<2>(T_H, HC_Q, j, Q);
             // after at least one iteration the z of the equality rows is their right-hand side
             for (int r = 0; r < 3; ++r)
-                acc_row(v, ax[j][r], tm_ld1(c.tm, j * T_STRIDE + T_H + HC_BE + r), c.ld(K_EEI + r, j));
+                acc_row(v, ax[j][r], c.hld1(T_H, HC_BE + r, j), c.ld(K_EEI + r, j));
             for (int e = 0; e < 5; ++e) {
                 acc_row(v, S5[e] * x[j][e], zb[j][e], c.ld(K_EBI + e, j));
                 VD q = (e >= 3) ? Q[e - 3] : VD(0.0);
@@ -1447,7 +1509,7 @@ struct ControlQP {
         AC_UNROLL
         for (int j = 0; j < C; ++j) {
             VD Q[2];
-            tm_ld<2>(c.tm, j * T_STRIDE + T_H + HC_Q, Q);
+            c.template hld<2>(T_H, HC_Q, j, Q);
             for (int e = 0; e < 5; ++e) {
                 VD di = c.ld(K_DI + e, j);
                 nrm = vmax(nrm, vabs(dx[j][e] / di));
@@ -1465,7 +1527,7 @@ struct ControlQP {
         for (int j = 0; j < C; ++j) {
             VD Hc[16], S5[8];
             c.tld(T_H, j, Hc);
-            tm_ld<8>(c.tm, j * T_STRIDE + T_G + GC_S, S5);
+            c.template hld<8>(T_G, GC_S, j, S5);
             for (int r = 0; r < 3; ++r) {   // equality rows: both bounds finite
                 VD a = adx[j][r] * c.ld(K_EEI + r, j);
                 bad = bad | (a > lim) | (a < -lim);
@@ -1529,6 +1591,7 @@ struct ControlQP {
         }
         warp_sync();
         factor();
+        AC_PHASE(c, 2);   // first factorisation
         Norms N;
         int status = 0, iter = 0, updates = 0;
         // same structure as SpeedQP::solve
@@ -1546,6 +1609,7 @@ struct ControlQP {
             if (iter == 1 || slow) {
                 if (iter == 1) iterate<true, true>();
                 else iterate<false, true>();
+                AC_PHASE(c, 3);   // iterations
                 if (slow) {
                     compute_norms(N);
                     if (checked) status = check(N, 0);
@@ -1562,6 +1626,7 @@ struct ControlQP {
                         if (uni(status == 0)) status = check(N, 1);
                         if (uni(status == 0)) status = ACMPC_MAX_ITER_REACHED;
                     }
+                    AC_PHASE(c, 4);   // termination checks (+ refactorisations)
                     if (uni(status != 0)) break;
                 }
             } else {
@@ -1576,7 +1641,7 @@ struct ControlQP {
             for (int e = 0; e < 5; ++e) {
                 VD xe = x[j][e];
                 obj = obj + VD(0.5) * c.ld(K_P + e, j) * xe * xe;
-                if (e >= 3) obj = obj + tm_ld1(c.tm, j * T_STRIDE + T_H + HC_Q + e - 3) * xe;
+                if (e >= 3) obj = obj + c.hld1(T_H, HC_Q + e - 3, j) * xe;
             }
         info.obj_val = final_obj(status, wsum(obj) * cinv);
         if (warm) {
@@ -1589,7 +1654,7 @@ struct ControlQP {
                 }
                 for (int r = 0; r < 3; ++r) {
                     st_lane(wrow + ((15 + r) * C + j) * 32, ye[j][r]);
-                    st_lane(wrow + ((18 + r) * C + j) * 32, tm_ld1(c.tm, j * T_STRIDE + T_H + HC_BE + r));
+                    st_lane(wrow + ((18 + r) * C + j) * 32, c.hld1(T_H, HC_BE + r, j));
                 }
             }
             AC_LANE0
@@ -1696,8 +1761,11 @@ AC_DEV void control_instance(const Ctx<C>& c, const double* raw_path, const doub
         c.st(F_XS, j, path.xs[j]), c.st(F_YS, j, path.ys[j]), c.st(F_PSI, j, path.psi[j]);
     }
     ControlQP<C> cq(c);
+    AC_PHASE(c, 0);   // waypoints
     cq.setup(path, vel, offset);
+    AC_PHASE(c, 1);   // setup (assembly + Ruiz)
     cq.solve(ci, warm, use_warm);
+    AC_PHASE(c, 6);   // end of solve (obj, warm store)
     // unpack (spatial_mpc.py:193-212) and roll out (dynamics.py:42-63)
     const double L = c.cfg->wheelbase;
     VD un[C][3], uv[C], uk[C];
@@ -1771,6 +1839,7 @@ AC_DEV void control_instance(const Ctx<C>& c, const double* raw_path, const doub
         warp_copy(o.derived, T, 3 * (n - 1));
     }
     warp_sync();   // the tile is the next instance's staging area
+    AC_PHASE(c, 7);   // outputs
     AC_LANE0
     {
         if (o.cost) *o.cost = ci.obj_val;

@@ -19,6 +19,7 @@
 #ifdef ACMPC_EMULATE
 // ------------------------------------------------------------------------------------------------
 #define AC_DEV static inline
+#define AC_HD
 #define AC_MEM inline
 #define AC_UNROLL
 #define AC_NOUNROLL
@@ -330,6 +331,7 @@ AC_DEV void warp_copy(double* dst, const double* src, int count)
 #else
 // ------------------------------------------------------------------------------------------------
 #define AC_DEV __device__ __forceinline__
+#define AC_HD __host__ __device__
 #define AC_MEM __device__ __forceinline__
 #define AC_UNROLL _Pragma("unroll")
 #define AC_NOUNROLL _Pragma("unroll 1")

@@ -395,7 +395,7 @@ def leg_nordschleife(fp64_peak, local_rank):
     # closed-loop replay: T steps of 2 m, warm records per instance, paths re-extracted on the device every step
     T = 6
     warm = mpc.alloc_warm(B)
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(T + 1)]
+    e = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(T)]
     M = cl.shape[0]
     step_idx = [torch.from_numpy(((idx.astype(np.int64) + 4 * t) % M).astype(np.int32)).to(dev) for t in range(T)]
     sample = np.random.default_rng(3).choice(B, 16, replace=False)
@@ -403,10 +403,11 @@ def leg_nordschleife(fp64_peak, local_rank):
     iters_equal, dmax, its, it_max, n_solved = True, 0.0, [], [], []
     torch.cuda.synchronize()
     for t in range(T):
-        e[t].record()
+        _FLUSH["t"].fill_(1)
+        e[t][0].record()
         mpc.extract_paths_device(d_cl, step_idx[t], out=d_paths)
         mpc.solve_device(d_paths, None, None, False, out=views, warm=warm)
-        e[t + 1].record()
+        e[t][1].record()
         torch.cuda.synchronize()
         got = {k: v.cpu().numpy() for k, v in views.items()}
         its.append(float(got["iters"][:, 1].mean()))
@@ -418,7 +419,7 @@ def leg_nordschleife(fp64_peak, local_rank):
             iters_equal = iters_equal and got["iters"][b].tolist() == want["iters"].tolist()
             if want["status"] == 1:
                 dmax = max(dmax, float(np.abs(got["controls"][b] - want["controls"]).max()))
-    warm_ms = [e[t].elapsed_time(e[t + 1]) for t in range(1, T)]
+    warm_ms = [e[t][0].elapsed_time(e[t][1]) for t in range(1, T)]
     mpc.close()
     return {"instances": int(B), "cold": {"value": cold_rate, "unit": UNIT, "ms_per_sweep": cold_ms,
                                            "solved_frac": float((cold["status"] == 1).mean()),

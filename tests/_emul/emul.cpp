@@ -17,16 +17,21 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
          int is_localised, const acmpc_outputs* out, double* warm, int use_warm)
 {
     const int H = cfg->horizon, n = H - 1;
+    using L = acmpc::Layout<C>;
     const size_t nd = (size_t)acmpc::smem_doubles<C>();
-    const size_t nt = (size_t)acmpc::Layout<C>::kTmemDoubles * 32;   // tensor-memory model: [double column][lane]
+    const size_t nt = (size_t)L::kTmemDoubles * 32;   // tensor-memory model: [double column][lane]
     double* smem = (double*)malloc(sizeof(double) * nd);
+    double* cold = (double*)malloc(sizeof(double) * (size_t)L::kColdDoubles);   // split layout: global memory
     double* tmem = (double*)malloc(sizeof(double) * nt);
     double* vel = (double*)malloc(sizeof(double) * (size_t)H);
     for (int b = 0; b < B; ++b) {
         memset(smem, 0xff, sizeof(double) * nd);   // NaN-poison
         memset(tmem, 0xff, sizeof(double) * nt);
         acmpc::Ctx<C> c;
-        c.S = smem, c.W = smem + acmpc::K_FIELDS * C * 32, c.tm.p = tmem, c.H = H, c.n = n, c.cfg = cfg;
+        c.S = L::kColdGlobal ? cold : smem;
+        c.W = L::kColdGlobal ? smem : smem + L::kColdDoubles;
+        c.HS = c.W + L::kScratch;
+        c.tm.p = tmem, c.H = H, c.n = n, c.cfg = cfg;
         c.lane = acmpc::lane_iota();
         double* raw = c.scratch();
         memcpy(raw, paths + (size_t)b * 3 * H, sizeof(double) * 3 * (size_t)H);
@@ -49,10 +54,12 @@ void run(const acmpc_config* cfg, int B, const double* paths, const double* offs
         double* wrec = warm ? warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;
         acmpc::speed_instance<C>(c, raw, vmax ? vmax[b] : cfg->v_max, is_localised, vel, o, wrec, use_warm != 0);
         memset(smem, 0xff, sizeof(double) * nd);
+        memset(cold, 0xff, sizeof(double) * (size_t)L::kColdDoubles);
         memcpy(raw, paths + (size_t)b * 3 * H, sizeof(double) * 3 * (size_t)H);
         acmpc::control_instance<C>(c, raw, vel, offsets ? offsets[b] : 0.0, o, wrec, use_warm != 0);
     }
     free(smem);
+    free(cold);
     free(tmem);
     free(vel);
 }
@@ -68,7 +75,7 @@ void run_speed(const acmpc_config* cfg, int B, double* way, const double* vmax, 
     for (int b = 0; b < B; ++b) {
         memset(smem, 0xff, sizeof(double) * nd);
         acmpc::Ctx<C> c;
-        c.S = nullptr, c.W = smem, c.tm.p = nullptr, c.H = H, c.n = n, c.cfg = cfg;
+        c.S = nullptr, c.HS = nullptr, c.W = smem, c.tm.p = nullptr, c.H = H, c.n = n, c.cfg = cfg;
         c.lane = acmpc::lane_iota();
         acmpc::InstanceOut o;
         memset(&o, 0, sizeof(o));
