@@ -321,6 +321,19 @@ struct Ctx {
         return tm_ld1(tm, Layout<C>::tmem_off(ch, j) + off);
     }
     AC_MEM void tld(int ch, int j, VD (&o)[16]) const { hld<16>(ch, 0, j, o); }
+    // several pieces of stage j at once; when all of them live in tensor memory the loads share ONE wait
+    template <int N0, int N1, int N2, int N3>
+    AC_MEM void hld4(int j, int c0, int f0, VD (&o0)[N0], int c1, int f1, VD (&o1)[N1], int c2, int f2, VD (&o2)[N2], int c3,
+                     int f3, VD (&o3)[N3]) const
+    {
+        using L = Layout<C>;
+        if (L::in_smem(c0, j) || L::in_smem(c1, j) || L::in_smem(c2, j) || L::in_smem(c3, j)) {
+            hld<N0>(c0, f0, j, o0), hld<N1>(c1, f1, j, o1), hld<N2>(c2, f2, j, o2), hld<N3>(c3, f3, j, o3);
+        } else {
+            tm_ld_group4<N0, N1, N2, N3>(tm, L::tmem_off(c0, j) + f0, o0, L::tmem_off(c1, j) + f1, o1, L::tmem_off(c2, j) + f2, o2,
+                                         L::tmem_off(c3, j) + f3, o3);
+        }
+    }
     AC_MEM void tst(int ch, int j, const VD (&v)[16]) const
     {
         if (Layout<C>::in_smem(ch, j)) {
@@ -1215,8 +1228,12 @@ struct ControlQP {
     AC_MEM void block_solve(const VD (&r)[C][3], VD (&xt)[C][3])
     {
         VD y[C][3], w[C][3], M[9], NS[C][16];
-        AC_UNROLL
-        for (int j = 0; j < C; ++j) c.tld(T_NS, j, NS[j]);
+        if (C == 2 && !Layout<C>::in_smem(T_NS, 0)) {   // both stages' factors under one tensor-memory wait
+            tm_ld_group2<16, 16>(c.tm, Layout<C>::tmem_off(T_NS, 0), NS[0], Layout<C>::tmem_off(T_NS, C - 1), NS[C - 1]);
+        } else {
+            AC_UNROLL
+            for (int j = 0; j < C; ++j) c.tld(T_NS, j, NS[j]);
+        }
         // forward: local pass with zero carry-in, scan over lanes, local fix-up
         VD Y[3] = {r[0][0], r[0][1], r[0][2]};
         AC_UNROLL
@@ -1316,12 +1333,10 @@ struct ControlQP {
             VD F[9], G[16], Q[8];   // F: rho[5] iv ik rb31 rb22 (no rinv here); Q: q[2] be[3] lb[0..2]
             {
                 VD f8[8], f1[1];
-                c.template hld<8>(T_F, 0, j, f8), c.template hld<1>(T_F, 8, j, f1);
+                c.template hld4<8, 1, 16, 8>(j, T_F, 0, f8, T_F, 8, f1, T_G, 0, G, T_H, HC_Q, Q);
                 for (int k = 0; k < 8; ++k) F[k] = f8[k];
                 F[8] = f1[0];
             }
-            c.tld(T_G, j, G);
-            c.template hld<8>(T_H, HC_Q, j, Q);
             const VD z0 = FIRST ? ze[j][0] : Q[HC_BE + 0], z1 = FIRST ? ze[j][1] : Q[HC_BE + 1],
                      z2 = FIRST ? ze[j][2] : Q[HC_BE + 2];
             VD w0 = VD(re) * z0 - ye[j][0], w1 = VD(re) * z1 - ye[j][1], w2 = VD(re) * z2 - ye[j][2];
@@ -1361,9 +1376,7 @@ struct ControlQP {
             VD F[16], G[10], Hc[16];   // of chunk G only s[5] m[3] b22 b31 are needed here (not A)
             {
                 VD g8[8], g2[2];
-                c.tld(T_F, j, F);
-                c.template hld<8>(T_G, 0, j, g8), c.template hld<2>(T_G, 8, j, g2);
-                c.tld(T_H, j, Hc);
+                c.template hld4<16, 8, 2, 16>(j, T_F, 0, F, T_G, 0, g8, T_G, 8, g2, T_H, 0, Hc);
                 for (int k = 0; k < 8; ++k) G[k] = g8[k];
                 G[8] = g2[0], G[9] = g2[1];
             }

@@ -319,6 +319,17 @@ AC_DEV VD tm_ld1(const Tm& t, int dcol)
     AC_FOR_LANES r.v[i_] = t.p[dcol * 32 + i_];
     return r;
 }
+// grouped loads (device: several tcgen05.ld under one wait)
+template <int N0, int N1, int N2, int N3>
+AC_DEV void tm_ld_group4(const Tm& t, int d0, VD (&o0)[N0], int d1, VD (&o1)[N1], int d2, VD (&o2)[N2], int d3, VD (&o3)[N3])
+{
+    tm_ld<N0>(t, d0, o0), tm_ld<N1>(t, d1, o1), tm_ld<N2>(t, d2, o2), tm_ld<N3>(t, d3, o3);
+}
+template <int N0, int N1>
+AC_DEV void tm_ld_group2(const Tm& t, int d0, VD (&o0)[N0], int d1, VD (&o1)[N1])
+{
+    tm_ld<N0>(t, d0, o0), tm_ld<N1>(t, d1, o1);
+}
 AC_DEV void warp_sync() {}
 // dst[0..count) = src[0..count), the warp's lanes taking consecutive elements (coalesced rows on the device)
 AC_DEV void warp_copy(double* dst, const double* src, int count)
@@ -547,6 +558,62 @@ AC_DEV void tm_st_raw16(uint32_t addr, const double* v)
                  : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(addr)
                  : "memory");
 }
+// Grouped loads: several tcgen05.ld issued back to back under ONE tcgen05.wait::ld, so a phase that needs three or four
+// chunks of a stage exposes the tensor-memory latency once instead of once per chunk.
+AC_DEV void tm_ld_group_8_1_16_8(uint32_t a0, double (&o0)[8], uint32_t a1, double (&o1)[1], uint32_t a2, double (&o2)[16], uint32_t a3, double (&o3)[8])
+{
+    uint32_t r[66];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%66];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%16,%17}, [%67];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49}, [%68];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63,%64,%65}, [%69];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63]), "=r"(r[64]), "=r"(r[65])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3)
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o0[k] = __hiloint2double((int)r[0 + 2 * k + 1], (int)r[0 + 2 * k]);
+#pragma unroll
+    for (int k = 0; k < 1; ++k) o1[k] = __hiloint2double((int)r[16 + 2 * k + 1], (int)r[16 + 2 * k]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o2[k] = __hiloint2double((int)r[18 + 2 * k + 1], (int)r[18 + 2 * k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o3[k] = __hiloint2double((int)r[50 + 2 * k + 1], (int)r[50 + 2 * k]);
+}
+AC_DEV void tm_ld_group_16_8_2_16(uint32_t a0, double (&o0)[16], uint32_t a1, double (&o1)[8], uint32_t a2, double (&o2)[2], uint32_t a3, double (&o3)[16])
+{
+    uint32_t r[84];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%84];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47}, [%85];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%48,%49,%50,%51}, [%86];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63,%64,%65,%66,%67,%68,%69,%70,%71,%72,%73,%74,%75,%76,%77,%78,%79,%80,%81,%82,%83}, [%87];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63]), "=r"(r[64]), "=r"(r[65]), "=r"(r[66]), "=r"(r[67]), "=r"(r[68]), "=r"(r[69]), "=r"(r[70]), "=r"(r[71]), "=r"(r[72]), "=r"(r[73]), "=r"(r[74]), "=r"(r[75]), "=r"(r[76]), "=r"(r[77]), "=r"(r[78]), "=r"(r[79]), "=r"(r[80]), "=r"(r[81]), "=r"(r[82]), "=r"(r[83])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3)
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o0[k] = __hiloint2double((int)r[0 + 2 * k + 1], (int)r[0 + 2 * k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o1[k] = __hiloint2double((int)r[32 + 2 * k + 1], (int)r[32 + 2 * k]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) o2[k] = __hiloint2double((int)r[48 + 2 * k + 1], (int)r[48 + 2 * k]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o3[k] = __hiloint2double((int)r[52 + 2 * k + 1], (int)r[52 + 2 * k]);
+}
+AC_DEV void tm_ld_group_16_16(uint32_t a0, double (&o0)[16], uint32_t a1, double (&o1)[16])
+{
+    uint32_t r[64];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n\t"
+                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                 : "r"(a0), "r"(a1)
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o0[k] = __hiloint2double((int)r[0 + 2 * k + 1], (int)r[0 + 2 * k]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o1[k] = __hiloint2double((int)r[32 + 2 * k + 1], (int)r[32 + 2 * k]);
+}
 template <int N>
 AC_DEV void tm_ld(const Tm& t, int dcol, double (&o)[N])
 {
@@ -574,6 +641,31 @@ AC_DEV double tm_ld1(const Tm& t, int dcol)
     double o[1];
     tm_ld_raw1(t.a + 2u * (uint32_t)dcol, o);
     return o[0];
+}
+// grouped loads: the shapes the ADMM iteration uses
+template <int N0, int N1, int N2, int N3>
+AC_DEV void tm_ld_group4(const Tm& t, int d0, double (&o0)[N0], int d1, double (&o1)[N1], int d2, double (&o2)[N2], int d3,
+                         double (&o3)[N3]);
+template <>
+AC_DEV void tm_ld_group4<8, 1, 16, 8>(const Tm& t, int d0, double (&o0)[8], int d1, double (&o1)[1], int d2, double (&o2)[16],
+                                      int d3, double (&o3)[8])
+{
+    tm_ld_group_8_1_16_8(t.a + 2u * (uint32_t)d0, o0, t.a + 2u * (uint32_t)d1, o1, t.a + 2u * (uint32_t)d2, o2,
+                         t.a + 2u * (uint32_t)d3, o3);
+}
+template <>
+AC_DEV void tm_ld_group4<16, 8, 2, 16>(const Tm& t, int d0, double (&o0)[16], int d1, double (&o1)[8], int d2, double (&o2)[2],
+                                       int d3, double (&o3)[16])
+{
+    tm_ld_group_16_8_2_16(t.a + 2u * (uint32_t)d0, o0, t.a + 2u * (uint32_t)d1, o1, t.a + 2u * (uint32_t)d2, o2,
+                          t.a + 2u * (uint32_t)d3, o3);
+}
+template <int N0, int N1>
+AC_DEV void tm_ld_group2(const Tm& t, int d0, double (&o0)[N0], int d1, double (&o1)[N1]);
+template <>
+AC_DEV void tm_ld_group2<16, 16>(const Tm& t, int d0, double (&o0)[16], int d1, double (&o1)[16])
+{
+    tm_ld_group_16_16(t.a + 2u * (uint32_t)d0, o0, t.a + 2u * (uint32_t)d1, o1);
 }
 AC_DEV void warp_sync() { __syncwarp(); }
 AC_DEV void warp_copy(double* dst, const double* src, int count)
