@@ -571,6 +571,15 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         dist.barrier()
     torch.cuda.synchronize()
     mpc.set_profiling(True)        # events around each of the two kernels, on the launching stream
+    if world > 1:
+        # Ranks leave an NCCL barrier up to a few hundred microseconds apart, and rank 0's timed region ends only when the
+        # LAST rank's results have landed: with 12 ms regions that skew alone is 1-3 % of the figure.  All ranks of one node
+        # share CLOCK_MONOTONIC, so rank 0 publishes a deadline 3 ms ahead and everybody starts on it.
+        go = torch.tensor([time.monotonic_ns() + 3_000_000], dtype=torch.int64, device=dev)
+        dist.broadcast(go, src=0)
+        go = int(go.item())
+        while time.monotonic_ns() < go:
+            pass
     sampler.mark()
     start, marks, end, views = timed_pass(K, n_warm)
     torch.cuda.synchronize()
