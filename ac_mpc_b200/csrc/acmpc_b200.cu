@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(32, OCC) acmpc_speed_kernel(const __grid_const
         if (lane == 0) {
             uint32_t v;
             for (;;) {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.credit_wait) : "memory");
+                // relaxed is enough: the stores this guards come after a branch on the loaded value, and the word only grows
+                asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.credit_wait) : "memory");
                 if (v >= p.credit_need) break;
                 __nanosleep(200);
             }
@@ -303,11 +304,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C <= 3 ? 2 :
         item = next < (uint32_t)p.B ? (int)next : p.B;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    if (p.flag) __threadfence_system();   // this thread's output stores (possibly to a peer GPU) before the CTA signs off
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kCols) : "memory");
     if (p.flag && threadIdx.x == 0) {
+        // ONE system-scope fence per CTA: the barrier above orders every thread's output stores (possibly to a peer GPU)
+        // before this point and fences are cumulative, so the release below covers them all (the grid-sync pattern).
+        // A fence in every thread cost 15 us per launch.
         __threadfence_system();
         const unsigned prev = atomicAdd(p.done, 1u);
         if (prev == gridDim.x - 1) {      // last CTA of the launch: everybody's stores are ordered before this point
