@@ -236,6 +236,9 @@ __global__ void __launch_bounds__(32, OCC) acmpc_speed_kernel(const __grid_const
     c.tm.a = 0;
     c.H = H, c.n = n, c.cfg = &p.cfg, c.lane = lane;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(c.W + acmpc::Layout<C>::kSpeedDoubles);
+#ifdef ACMPC_PHASE_TIMING
+    c.tl = clock64();
+#endif
     if (!p.way) stage_path(c.W, p.paths + (size_t)b * 3 * H, H, p.use_tma, mbar, lane);
     const double vmax = p.vmax ? p.vmax[b] : p.cfg.v_max;
     double* wrec = p.warm ? p.warm + (size_t)b * acmpc::Layout<C>::kWarmDoubles : nullptr;

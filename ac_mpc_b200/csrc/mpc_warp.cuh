@@ -831,6 +831,7 @@ struct SpeedQP {
         }
         warp_sync();
         factor();
+        AC_PHASE(c, 10);   // first factorisation
         Norms N;
         int status = 0, iter = 0, updates = 0;
         // osqp_solve's order: iterate -> exact check (every check_termination iterations) -> adaptive rho;
@@ -852,6 +853,7 @@ struct SpeedQP {
             last = iter >= g.max_iter;
             if (checked || adapt || last) {
                 iterate<true>(alpha, sigma);
+                AC_PHASE(c, 11);   // iterations
                 compute_norms(N);
                 if (checked) status = check(N, 0);
                 if (uni(status == 0) && adapt) {
@@ -867,6 +869,7 @@ struct SpeedQP {
                     if (uni(status == 0)) status = check(N, 1);
                     if (uni(status == 0)) status = ACMPC_MAX_ITER_REACHED;
                 }
+                AC_PHASE(c, 12);   // checks
                 if (uni(status != 0)) break;
             } else {
                 iterate<false>(alpha, sigma);
@@ -1718,8 +1721,11 @@ AC_DEV int speed_instance(const Ctx<C>& c, const double* raw_path, double v_max_
     SolveInfo si;
     VD vel[C];
     SpeedQP<C> sq(c);
+    AC_PHASE(c, 8);    // speed kernel: staging + waypoints
     sq.assemble_and_scale(path, v_max_live, localised);
+    AC_PHASE(c, 9);    // assembly + Ruiz
     sq.solve(si, vel, warm, localised ? 1 : 0, use_warm);
+    AC_PHASE(c, 13);   // solve tail
     // Outputs leave as coalesced rows: lane l owns stages C*l .., a stride-C pattern that would write half-empty
     // sectors (and, when the outputs are peer-mapped, one small NVLink write each); every row goes through a
     // shared-memory tile and is written out lane-contiguous.  The scratch region is dead after the solve.
@@ -1746,6 +1752,7 @@ AC_DEV int speed_instance(const Ctx<C>& c, const double* raw_path, double v_max_
         }
         if (o.v_ref && o.v_ref != vel_out) row(o.v_ref, vel);
     }
+    AC_PHASE(c, 14);   // outputs
     AC_LANE0
     {
         if (o.status_speed) *o.status_speed = si.status;

@@ -14,7 +14,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "tools", "_exp", "libacmpc_phase.so")
 NAMES = ["waypoints", "setup (assembly + Ruiz)", "first factorisation", "ADMM iterations", "checks (+ refactor)", "-",
-         "solve tail (obj, warm)", "outputs"]
+         "solve tail (obj, warm)", "outputs",
+         "SPEED: staging + waypoints", "SPEED: assembly + Ruiz", "SPEED: first factorisation", "SPEED: ADMM iterations",
+         "SPEED: checks (+ refactor)", "SPEED: solve tail", "SPEED: outputs"]
 
 if sys.argv[1] == "build":
     os.makedirs(os.path.dirname(SO), exist_ok=True)
@@ -43,10 +45,11 @@ else:
         torch.cuda.synchronize()
         lib.acmpc_exp_phase_cycles(buf)
     cyc = np.array(list(buf), dtype=np.float64)
-    tot = cyc.sum()
-    print(f"B={B} H={H}: {tot / B:.0f} cycles per instance (lane-0 clock64 deltas, summed over phases)")
-    for k, nm in enumerate(NAMES):
-        if cyc[k] > 0:
-            print(f"  {nm:28s} {cyc[k] / B:10.0f} cycles  {100 * cyc[k] / tot:5.1f} %")
+    for lo, hi, what in ((0, 8, "control kernel"), (8, 16, "speed kernel")):
+        tot = cyc[lo:hi].sum()
+        print(f"B={B} H={H} {what}: {tot / B:.0f} cycles per instance (lane-0 clock64 deltas, summed over phases)")
+        for k in range(lo, min(hi, len(NAMES))):
+            if cyc[k] > 0:
+                print(f"  {NAMES[k]:30s} {cyc[k] / B:10.0f} cycles  {100 * cyc[k] / tot:5.1f} %")
     it = views["iters"].cpu().numpy()
-    print("  mean control iterations", it[:, 1].mean())
+    print("  mean iterations (speed, control)", it[:, 0].mean(), it[:, 1].mean())
