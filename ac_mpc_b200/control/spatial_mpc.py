@@ -49,6 +49,7 @@ class SpatialMPC:
         self._osqp_overrides = dict(osqp_overrides)
         self._solver: Optional[BatchedMPC] = None      # created lazily (fork safety, controller.py:293)
         self._solver_key = None
+        self._out1 = self._out1_solver = None
         self.last_info: Dict = {}
 
     # ------------------------------------------------------------------------------------------
@@ -85,7 +86,14 @@ class SpatialMPC:
         """One MPC step; signature and side effects of spatial_mpc.py:170-217."""
         path = np.ascontiguousarray(reference_path, dtype=np.float64)[None]
         # the reference keeps its OSQP objects between calls (warm start, carried rho): so does the handle
-        out = self.get_control_batch(path, np.array([float(offset)]), None, is_localised, keep_warm=True)
+        # one set of output arrays per object, reused by every call (the attributes below are copies)
+        solver = self._batched()
+        if self._out1 is None or self._out1_solver is not solver:
+            self._out1, self._out1_solver = solver.alloc_host_outputs(1), solver
+            self._off1, self._vmax1 = np.zeros(1), np.zeros(1)
+        self._off1[0] = float(offset)
+        self._vmax1[0] = float(self.speed_profile_constraints["v_max"])
+        out = solver.solve_host(path, self._off1, self._vmax1, is_localised, out=self._out1, keep_warm=True)
         n = self.MPC_horizon - 1
         status, status_speed = int(out["status"][0]), int(out["status_speed"][0])
         self.last_info = dict(status=_capi.STATUS_STRINGS.get(status, str(status)),

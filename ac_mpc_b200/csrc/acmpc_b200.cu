@@ -928,13 +928,17 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
             if (field_ptr(*out, f)) field_ptr(d, f) = base + o_f[f] + z * per_b[f];
         return d;
     };
-    // Small batches (the B = 1 drop-in call): inputs and outputs go through ONE pinned staging buffer that mirrors
-    // the arena -- one H2D, the kernels, one D2H, then plain memcpys -- instead of 3 + 14 separate copies.
+    // Small batches (the B = 1 drop-in call) are ZERO-COPY: inputs and outputs live in ONE pinned staging buffer that
+    // mirrors the arena layout and the kernels read / write it directly over PCIe (UVA: pinned host memory is device
+    // accessible under the same pointer) -- no cudaMemcpy at all, two launches and one stream synchronisation.  An
+    // instance moves 1.2 KB in and 2.4-6 KB out, far too little for a copy engine round trip to pay (the two staged
+    // copies cost ~20 us of a 0.24 ms call).  Only the speed-profile hand-over between the kernels stays in the arena.
     if (B <= 64) {
         if (off > h->stage_bytes) {
+            if (fail(h, cudaStreamSynchronize(h->streams[0]), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
             if (h->h_stage) cudaFreeHost(h->h_stage);
             h->h_stage = nullptr, h->stage_bytes = 0;
-            if (fail(h, cudaHostAlloc(&h->h_stage, off, cudaHostAllocDefault), "cudaHostAlloc(stage)")) return ACMPC_ERR_CUDA;
+            if (fail(h, cudaHostAlloc(&h->h_stage, off, cudaHostAllocMapped), "cudaHostAlloc(stage)")) return ACMPC_ERR_CUDA;
             h->stage_bytes = off;
         }
         char* st = static_cast<char*>(h->h_stage);
@@ -942,21 +946,15 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
         memcpy(st + o_paths, paths, nb * 3 * H * 8);
         if (offsets) memcpy(st + o_off, offsets, nb * 8);
         if (vmax) memcpy(st + o_vmax, vmax, nb * 8);
-        if (fail(h, cudaMemcpyAsync(base, st, o_f[0], cudaMemcpyHostToDevice, s), "H2D inputs")) return ACMPC_ERR_CUDA;
-        const acmpc_outputs d = device_outputs(0);
-        int rc = launch(h, B, reinterpret_cast<const double*>(base + o_paths),
-                        offsets ? reinterpret_cast<const double*>(base + o_off) : nullptr,
-                        vmax ? reinterpret_cast<const double*>(base + o_vmax) : nullptr, is_localised, &d,
+        acmpc_outputs d;
+        memset(&d, 0, sizeof(d));
+        for (int f = 0; f < kNumFields; ++f)
+            if (field_ptr(*out, f)) field_ptr(d, f) = st + o_f[f];
+        int rc = launch(h, B, reinterpret_cast<const double*>(st + o_paths),
+                        offsets ? reinterpret_cast<const double*>(st + o_off) : nullptr,
+                        vmax ? reinterpret_cast<const double*>(st + o_vmax) : nullptr, is_localised, &d,
                         reinterpret_cast<double*>(base + o_f[kFieldVref]), static_cast<double*>(h->d_warm), 1, s, 0);
         if (rc != ACMPC_OK) return rc;
-        // the requested fields form a sub-range of the arena's output region: copy from its first to its last byte
-        int f_lo = kNumFields, f_hi = -1;
-        for (int f = 0; f < kNumFields; ++f)
-            if (field_ptr(*out, f)) f_lo = f < f_lo ? f : f_lo, f_hi = f;
-        if (f_hi >= 0) {
-            const size_t lo = o_f[f_lo], hi = o_f[f_hi] + nb * per_b[f_hi];
-            if (fail(h, cudaMemcpyAsync(st + lo, base + lo, hi - lo, cudaMemcpyDeviceToHost, s), "D2H outputs")) return ACMPC_ERR_CUDA;
-        }
         if (fail(h, cudaStreamSynchronize(s), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
         for (int f = 0; f < kNumFields; ++f)
             if (field_ptr(*out, f)) memcpy(field_ptr(*out, f), st + o_f[f], nb * per_b[f]);

@@ -51,6 +51,7 @@ class BatchedMPC:
         self.n = self.H - 1
         self._h = None
         self._lib = _capi.load()
+        self._checked_out = (None, 0, None)
 
     # -- lifetime -------------------------------------------------------------------------------
     def _handle(self):
@@ -145,12 +146,20 @@ class BatchedMPC:
                 raise ValueError(f"{nm} must have shape ({B},)")
         if out is None:
             out = self.alloc_host_outputs(B, fields)
+        elif out is not self._checked_out[0] or B != self._checked_out[1]:
+            self._check_host_outputs(out, B)       # once per buffer set: a control loop reuses the same arrays
+            o = _capi.Outputs()
+            for name in _capi.OUTPUT_FIELDS:
+                if name in out:
+                    setattr(o, name, out[name].ctypes.data)
+            self._checked_out = (out, B, o)
+        if out is self._checked_out[0]:
+            o = self._checked_out[2]
         else:
-            self._check_host_outputs(out, B)
-        o = _capi.Outputs()
-        for name in _capi.OUTPUT_FIELDS:
-            if name in out:
-                setattr(o, name, out[name].ctypes.data)
+            o = _capi.Outputs()
+            for name in _capi.OUTPUT_FIELDS:
+                if name in out:
+                    setattr(o, name, out[name].ctypes.data)
         dp = C.POINTER(C.c_double)
         ptr = lambda a: a.ctypes.data_as(dp) if a is not None else None
         self._check(self._lib.acmpc_solve_batch_host(self._handle(), B, ptr(paths), ptr(offsets), ptr(vmax),
