@@ -960,6 +960,34 @@ int32_t acmpc_solve_batch_host(acmpc_handle* h, int32_t B, const double* paths, 
             if (field_ptr(*out, f)) memcpy(field_ptr(*out, f), st + o_f[f], nb * per_b[f]);
         return ACMPC_OK;
     }
+    // Large batches whose buffers are ALL pinned host memory (cudaHostAlloc / cudaHostRegister: what a control loop that
+    // cares about latency uses, and what bench.py's e2e leg passes) are zero-copy as well: one launch over the whole
+    // batch, the speed kernel pulls the paths over PCIe (4.9 MB per 4096 instances, hidden behind its 16 warps per SM),
+    // the kernels push their results straight into the caller's arrays (23 GB/s at 4096 instances per 0.42 ms), and the
+    // call ends with one stream synchronisation.  ACMPC_ZEROCOPY=0 forces the staged, chunk-pipelined path below.
+    {
+        static const int zc_env = [] { const char* e = getenv("ACMPC_ZEROCOPY"); return (e && e[0] == '0') ? 0 : 1; }();
+        auto pinned = [](const void* ptr) {
+            if (!ptr) return true;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            return at.type == cudaMemoryTypeHost;
+        };
+        bool zc = zc_env && pinned(paths) && pinned(offsets) && pinned(vmax);
+        for (int f = 0; zc && f < kNumFields; ++f) zc = pinned(field_ptr(*out, f));
+        if (zc) {
+            cudaStream_t s = h->streams[0];
+            if (!ensure_order(h, 0, B)) return ACMPC_ERR_CUDA;
+            int rc = launch(h, B, paths, offsets, vmax, is_localised, out,
+                            reinterpret_cast<double*>(base + o_f[kFieldVref]), static_cast<double*>(h->d_warm), 1, s, 0);
+            if (rc != ACMPC_OK) return rc;
+            if (fail(h, cudaStreamSynchronize(s), "cudaStreamSynchronize")) return ACMPC_ERR_CUDA;
+            return ACMPC_OK;
+        }
+    }
     // Large batches go through as up to 4 chunks on 4 streams (own ticket queue each), so that the H2D copy of
     // one chunk and the D2H copy of another overlap the kernels of a third.  (Async only from pinned host memory.)
     // 2 chunks from 512 instances, 4 from 2048 (measured at 4096: 1 / 2 / 3 / 4 / 6 / 8 chunks = 4.31 / 5.04 / 5.12 / 5.36 /
