@@ -276,7 +276,23 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C <= 3 ? 2 :
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // optionally persistent warps: the first instance is the warp's global index, further ones come from the
     // queue, so a warp whose instance converges early does not idle behind its CTA's slowest one
-    for (int item = blockIdx.x * kWarpsPerCta + warp; item < p.B;) {
+    // C = 3: the hot loop is 1.5x the C = 2 one and no longer fits the instruction cache once the 8 warps of an SM sit in
+    // 8 different phases of it (ncu, H = 80: 34 % of the stall samples were `no_instructions`).  There the four warps of a
+    // CTA stay IN PHASE instead: the CTA draws four instances at a time and meets at a barrier between rounds, so an SM
+    // executes two code positions, not eight -- at the price of waiting for the slowest of four instances.
+    constexpr bool kPhased = (C == 3);
+    __shared__ uint32_t cta_ticket;
+    uint32_t round_base = blockIdx.x * kWarpsPerCta;
+    for (int item = blockIdx.x * kWarpsPerCta + warp; kPhased ? (round_base < (uint32_t)p.B) : (item < p.B);) {
+        if (kPhased && item >= p.B) {   // a partial last round: this warp has no instance but keeps the barriers
+            __syncthreads();
+            if (threadIdx.x == 0) cta_ticket = atomicAdd(p.queue, (uint32_t)kWarpsPerCta);
+            __syncthreads();
+            const uint32_t nx = (cta_ticket - p.queue_base) + p.warps_launched;
+            round_base = nx < (uint32_t)p.B ? nx : (uint32_t)p.B;
+            item = (int)round_base + warp;
+            continue;
+        }
         const int b = p.order ? ordered_instance(p.order + 8 * p.order_set + 4, p.order + 16 + (size_t)kOrderBins * p.B,
                                                  p.B, item)
                               : item;
@@ -300,6 +316,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, (C == 1 ? 3 : (C <= 3 ? 2 :
         acmpc::control_instance<C>(c, c.W, p.vel + (size_t)b * n, offset, slice_outputs(p.out, b, H), wrec,
                                    p.use_warm != 0);
         if (!p.persistent) break;
+        if (kPhased) {
+            __syncthreads();
+            if (threadIdx.x == 0) cta_ticket = atomicAdd(p.queue, (uint32_t)kWarpsPerCta);
+            __syncthreads();
+            const uint32_t nx = (cta_ticket - p.queue_base) + p.warps_launched;
+            round_base = nx < (uint32_t)p.B ? nx : (uint32_t)p.B;
+            item = (int)round_base + warp;
+            continue;
+        }
         uint32_t ticket = 0;
         if (lane == 0) ticket = atomicAdd(p.queue, 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
@@ -566,7 +591,9 @@ int launch(acmpc_handle* h, int B, const double* d_paths, const double* d_offset
     if (ev) cudaEventRecord(ev[2], stream);
     // host-side mirrors of the device counters move only once both kernels are in the stream: a failed launch leaves
     // the ticket base and the counter-set parity where the device still has them
-    if (p.persistent) h->queue_pos[qi] += (uint32_t)B;   // every solved instance draws one ticket
+    // every solved instance draws one ticket; the phased C = 3 kernel draws four per CTA round, partial rounds included
+    if (p.persistent)
+        h->queue_pos[qi] += stages_per_lane(H) == 3 ? (uint32_t)((B + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta) : (uint32_t)B;
     if (p.order) h->order_parity[qi] = p.order_set;
     h->last_launches += 2, h->last_smem = (int)smem, h->last_threads = 32 * kWarpsPerCta, h->last_ipc = kWarpsPerCta;
     if (fail(h, cudaGetLastError(), "kernel launch")) return ACMPC_ERR_CUDA;

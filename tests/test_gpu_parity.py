@@ -192,6 +192,21 @@ def test_work_queue_across_launches_of_one_handle():
         _assert_equals_oracle(got, want, fields=("controls", "cost"))
 
 
+def test_work_queue_of_the_phased_kernel_across_ragged_launches():
+    """Horizons 65..96 run the split layout with CTA-phased rounds (four tickets per CTA round, partial rounds included):
+    launches whose sizes are not multiples of four, smaller than one CTA, larger than the device holds, on ONE handle."""
+    import _golden
+
+    kw = _golden.racing_kwargs("spa", 80)
+    mpc = _solver(**kw)
+    cfg = port.default_config(**kw)
+    for B, seed in ((1, 3), (3001, 4), (7, 5), (2, 7), (2375, 8), (5, 9)):
+        paths, vmax = tracks.perturbed_batch("spa", B, horizon=80, seed=seed)
+        got = mpc.solve_host(paths, None, vmax)
+        want = port.solve_batch(cfg, paths, None, vmax, nthreads=16)
+        _assert_equals_oracle(got, want, fields=("controls", "cost"))
+
+
 def test_baseline_config3_nordschleife_every_waypoint_sweep():
     """BASELINE.json configs[2]: one instance per metre of the Nordschleife centreline (~20.8 k instances,
     unperturbed), every instance checked against the oracle (the C port does the sweep in under a second)."""
