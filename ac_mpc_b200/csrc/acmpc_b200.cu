@@ -462,6 +462,17 @@ size_t warm_bytes_for(int H)
     }
 }
 
+// Shared-memory carve-out of the control kernel.  Horizons up to 96 fill an SM's shared memory with their 2-3 CTAs: maximum
+// carve-out.  C = 4 (H >= 97) fits ONE CTA (155 KB) and spills registers heavily (84 doubles of iterates per lane): it asks
+// only for what that CTA needs, so the rest of the 256 KB stays L1 and catches the spills instead of sending them to L2.
+int carveout_percent_for(int H, int smem_per_sm)
+{
+    if (stages_per_lane(H) < 4) return cudaSharedmemCarveoutMaxShared;
+    const size_t need = smem_bytes_for(H) + 2048;
+    int pct = (int)((need * 100 + (size_t)smem_per_sm - 1) / (size_t)smem_per_sm);
+    return pct > 100 ? 100 : pct;
+}
+
 size_t cold_doubles_for(int H)   // per warp, 0 unless the horizon's layout keeps the cold fields in global memory
 {
     switch (stages_per_lane(H)) {
@@ -797,7 +808,7 @@ int32_t acmpc_create(const acmpc_config* cfg, int32_t device, acmpc_handle** out
                                      (int)speed_smem_bytes_for(cfg->horizon)),
              "cudaFuncSetAttribute(speed, dense)") ||
         fail(h, cudaFuncSetAttribute(kernel_for(cfg->horizon), cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared),
+                                     carveout_percent_for(cfg->horizon, (int)prop.sharedMemPerMultiprocessor)),
              "cudaFuncSetAttribute(carveout)") ||
         fail(h, cudaMalloc(&h->d_queue, kSlots * sizeof(uint32_t)), "cudaMalloc(queue)") ||
         fail(h, cudaMemset(h->d_queue, 0, kSlots * sizeof(uint32_t)), "cudaMemset(queue)") ||
