@@ -5,6 +5,7 @@ behind a C ABI (include/acmpc_b200.h).  See DESIGN.md / INTEGRATION.md.
 """
 from . import tracks  # noqa: F401
 from ._capi import STATUS_STRINGS, Config, default_config  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 from .solver import BatchedMPC, config_from_reference, fp64_peak_tflops  # noqa: F401
 
 __version__ = "0.1.0"

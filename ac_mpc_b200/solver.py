@@ -510,6 +510,13 @@ class BatchedMPC:
         s = torch.cuda.current_stream(self.device) if stream is None else stream
         self._check(self._lib.acmpc_stream_wait_value32(self._handle(), C.c_void_p(addr), int(value), C.c_void_p(s.cuda_stream)))
 
+    def pipeline(self, B: int, fields=None, depth: int = 2):
+        """A HostPipeline (ac_mpc_b200/pipeline.py) over this solver: submit()/wait() for streams of B-instance batches,
+        the H2D / kernels / D2H of consecutive batches overlapped."""
+        from .pipeline import HostPipeline
+
+        return HostPipeline(self, B, fields, depth)
+
     def solve_device(self, paths, offsets=None, vmax=None, is_localised: bool = False, out=None, stream=None,
                      warm=None, warm_valid: bool = True):
         """DEVICE tensors in/out (acmpc_solve_batch_device); asynchronous on `stream` (torch stream or

@@ -207,6 +207,36 @@ def test_work_queue_of_the_phased_kernel_across_ragged_launches():
         _assert_equals_oracle(got, want, fields=("controls", "cost"))
 
 
+def test_host_pipeline_overlaps_batches_without_mixing_them_up():
+    """HostPipeline: several different batches in flight (H2D / kernels / D2H of consecutive batches overlap), pinned and
+    plain inputs; every batch must come back bit-equal to the synchronous call on the same inputs."""
+    import torch
+
+    mpc = _solver()
+    B = 3000
+    fields = ["controls", "prediction", "cum_time", "status", "iters", "cost"]
+    pipe = mpc.pipeline(B, fields, depth=2)
+    batches = []
+    for seed in range(5):
+        p, v = tracks.perturbed_batch("monza", B, seed=40 + seed)
+        o = np.random.default_rng(seed).uniform(-0.3, 0.3, B)
+        if seed & 1:
+            p, v = torch.from_numpy(p).pin_memory().numpy(), torch.from_numpy(v).pin_memory().numpy()
+        batches.append((p, o, v, bool(seed == 3)))
+    want = [_solver().solve_host(p, o, v, loc, fields=fields) for p, o, v, loc in batches]
+    tickets, got = [], []
+    for i, (p, o, v, loc) in enumerate(batches):
+        tickets.append(pipe.submit(p, o, v, loc))
+        if i >= 1:
+            got.append({k: a.copy() for k, a in pipe.wait(tickets[i - 1]).items()})
+    got.append({k: a.copy() for k, a in pipe.wait(tickets[-1]).items()})
+    for g, w in zip(got, want):
+        for k in fields:
+            assert np.array_equal(g[k], w[k]), k
+    with pytest.raises(ValueError):
+        pipe.wait(tickets[0])          # long out of flight
+
+
 def test_baseline_config3_nordschleife_every_waypoint_sweep():
     """BASELINE.json configs[2]: one instance per metre of the Nordschleife centreline (~20.8 k instances,
     unperturbed), every instance checked against the oracle (the C port does the sweep in under a second)."""
