@@ -88,6 +88,7 @@ class ShardedMPC:
         self._host_in = None
         self._host_out = None
         self._host_sizes = None
+        self._shm = None
         self._lv_cache, self._gv_cache, self._size_cache = {}, {}, {}
         self._last_B = 0
 
@@ -278,11 +279,21 @@ class ShardedMPC:
 
     # -- host global batch (the call a user makes) ------------------------------------------------------------------
     def solve(self, paths, offsets=None, vmax=None, is_localised: bool = False, local: bool = False,
-              B_total: Optional[int] = None) -> Optional[Dict[str, np.ndarray]]:
+              B_total: Optional[int] = None, deliver: str = "auto") -> Optional[Dict[str, np.ndarray]]:
         """HOST arrays in, HOST arrays out on dst.  `local=False`: every rank passes the same GLOBAL arrays and takes its
         own shard_range slice; `local=True`: each rank passes only its shard (then B_total = sum over ranks is required
-        unless all shards are equal).  Pinned staging buffers are kept between calls; synchronous."""
+        unless all shards are equal).  Pinned staging buffers are kept between calls; synchronous.
+
+        `deliver`: how the results reach dst's HOST memory.
+          "shm"      every rank copies its own shard over its OWN PCIe link into one host shared-memory segment that all
+                     ranks map and pin (the way the reference itself publishes results, `mp.Array` shared memory,
+                     controller.py:274-280): N links in parallel, nothing crosses NVLink, dst returns views of the segment;
+          "exchange" the device exchange (peer stores / NCCL gather) lands everything in dst's HBM and dst copies it out
+                     over its one PCIe link (79 MB per step at 8 x 4096 instances);
+          "auto"     "shm" on CUDA with more than one rank, else "exchange"."""
         torch = self._torch
+        if deliver == "auto":
+            deliver = "shm" if (self.cuda and self.world > 1) else "exchange"
         paths = np.asarray(paths, dtype=np.float64)
         if local:
             B = paths.shape[0]
@@ -319,6 +330,9 @@ class ShardedMPC:
             upload(do, ho, offsets)
         if vmax is not None:
             upload(dv, hv, vmax)
+        if deliver == "shm":
+            return self._solve_shm(dp, do if offsets is not None else None, dv if vmax is not None else None,
+                                   is_localised, B, B_total, lo, hi)
         t = self.submit_device(dp, do if offsets is not None else None, dv if vmax is not None else None, is_localised,
                                B_total=B_total)
         views = self.wait(t)
@@ -341,3 +355,173 @@ class ShardedMPC:
                 bufs[k][l:u].copy_(views[k][r], non_blocking=True)
         self.drain()
         return {k: bufs[k].numpy() for k in self.fields}
+
+    # -- host delivery through one shared-memory segment ------------------------------------------------------------
+    def _ensure_shm(self, B_total: int):
+        """Collective: one POSIX shared-memory file (two result buffers + a control page), mapped and pinned by every rank."""
+        import os
+        import uuid
+
+        torch, dist = self._torch, self._dist
+        if self._shm is not None and self._shm["B_total"] == B_total:
+            return self._shm
+        spec = _capi.output_spec(self.H)
+        offs, total = {}, 0
+        for k in self.fields:
+            shp, dt = spec[k]
+            nb = B_total * int(np.prod(shp, dtype=np.int64)) * np.dtype(dt).itemsize
+            offs[k] = (total, nb)
+            total = (total + nb + 4095) // 4096 * 4096
+        size = 2 * total + 4096
+        name = [uuid.uuid4().hex if self.rank == self.dst else None]
+        dist.broadcast_object_list(name, src=self.dst, group=self.group)
+        path = f"/dev/shm/acmpc_b200_{name[0]}"
+        if self.rank == self.dst:
+            with open(path, "wb") as f:
+                f.truncate(size)
+        dist.barrier(group=self.group)
+        mm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(size,))
+        dist.barrier(group=self.group)
+        if self.rank == self.dst:
+            os.unlink(path)                          # the mappings keep the segment alive
+        t = torch.from_numpy(mm)
+        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), size, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister of the shared result segment failed ({rc})")
+        bufs = []
+        for b in range(2):
+            tv, nv = {}, {}
+            for k in self.fields:
+                shp, dt = spec[k]
+                o, nb = offs[k]
+                seg = t[b * total + o: b * total + o + nb]
+                tv[k] = seg.view(getattr(torch, dt)).view((B_total,) + shp)
+                nv[k] = mm[b * total + o: b * total + o + nb].view(dt).reshape((B_total,) + shp)
+            bufs.append((tv, nv))
+        ctrl = mm[2 * total:].view(np.int64)          # [8 r] = steps rank r has delivered, [8 world] = steps dst has released
+        _, plain = self.solver.alloc_device_outputs(self._shard_cap(B_total), self.fields)
+        self._shm = dict(B_total=B_total, mm=mm, t=t, bufs=bufs, ctrl=ctrl, step=0, plain=plain)
+        return self._shm
+
+    def _shard_cap(self, B_total: int) -> int:
+        return max(h - l for l, h in (shard_range(B_total, r, self.world) for r in range(self.world)))
+
+    def _solve_shm(self, dp, do, dv, is_localised, B, B_total, lo, hi):
+        import time
+
+        torch = self._torch
+        sh = self._ensure_shm(B_total)
+        step, ctrl = sh["step"], sh["ctrl"]
+        buf = step & 1
+        if self.rank == self.dst:
+            ctrl[8 * self.world] = step               # results of every earlier call are released (valid until the next call)
+        else:
+            while ctrl[8 * self.world] < step - 1:    # buffer `buf` held step - 2: dst must have started step - 1
+                time.sleep(0)
+        views = {k: v[:B] for k, v in sh["plain"].items()}
+        self.solver.solve_device(dp, do, dv, is_localised, out=views)
+        tv, nv = sh["bufs"][buf]
+        for k in self.fields:
+            tv[k][lo:hi].copy_(views[k], non_blocking=True)     # this rank's shard, over this rank's PCIe link
+        torch.cuda.current_stream(self.device).synchronize()
+        ctrl[8 * self.rank] = step + 1
+        sh["step"] = step + 1
+        if self.rank != self.dst:
+            return None
+        for r in range(self.world):
+            while ctrl[8 * r] < step + 1:
+                pass
+        return nv
+
+    # -- streams of batches, host to host: every rank runs its own copy-in / compute / copy-out pipeline ---------------
+    def submit_host(self, paths, offsets=None, vmax=None, is_localised: bool = False, B_total: Optional[int] = None,
+                    depth: int = 2) -> int:
+        """Asynchronous `solve(local=True, deliver="shm")` for STREAMS of batches: this rank's shard (host arrays, pinned
+        for true asynchrony) goes up on a copy stream, is solved on a compute stream and its results go down this rank's
+        own PCIe link into the shared host segment on a third stream; consecutive steps overlap.  Every rank calls it;
+        `wait_host(ticket)` on dst returns whole-batch numpy views, valid until `depth` further submits."""
+        import time
+
+        torch = self._torch
+        paths = np.asarray(paths, dtype=np.float64)
+        B = paths.shape[0]
+        if B_total is None:
+            B_total = B * self.world
+        lo, hi = shard_range(B_total, self.rank, self.world)
+        if hi - lo != B:
+            raise ValueError("local shard size does not match shard_range(B_total, rank, world)")
+        sh = self._ensure_shm(B_total)
+        if "pipe" not in sh:
+            dev = self.device
+            slots = []
+            for _ in range(depth):
+                _, views = self.solver.alloc_device_outputs(B, self.fields)
+                slots.append(dict(d_paths=torch.empty((B, self.H, 3), dtype=torch.float64, device=dev),
+                                  d_off=torch.empty(B, dtype=torch.float64, device=dev),
+                                  d_vmax=torch.empty(B, dtype=torch.float64, device=dev),
+                                  h_paths=torch.empty((B, self.H, 3), dtype=torch.float64).pin_memory(),
+                                  h_off=torch.empty(B, dtype=torch.float64).pin_memory(),
+                                  h_vmax=torch.empty(B, dtype=torch.float64).pin_memory(),
+                                  views=views, in_ready=torch.cuda.Event(), solved=torch.cuda.Event(),
+                                  out_done=torch.cuda.Event(), used=False))
+            sh["pipe"] = dict(slots=slots, depth=depth, streams=[torch.cuda.Stream(device=dev) for _ in range(3)],
+                              count=torch.zeros(1, dtype=torch.int64, device=dev),
+                              ctrl_t=sh["t"][2 * ((sh["t"].numel() - 4096) // 2):].view(torch.int64))
+            if depth != 2:
+                raise ValueError("the shared segment holds two result buffers: depth must be 2")
+        pp = sh["pipe"]
+        step, ctrl = sh["step"], sh["ctrl"]
+        s = pp["slots"][step % pp["depth"]]
+        s_in, s_run, s_out = pp["streams"]
+        if self.rank == self.dst:
+            ctrl[8 * self.world] = step - pp["depth"] + 1      # steps <= step - depth are released
+        else:
+            while ctrl[8 * self.world] < step - pp["depth"] + 1:
+                time.sleep(0)
+
+        def stage(buf, arr):
+            src = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+            if src.is_pinned():
+                return src
+            buf.copy_(src)
+            return buf
+
+        with torch.cuda.stream(s_in):
+            if s["used"]:
+                s_in.wait_event(s["solved"])
+            s["d_paths"].copy_(stage(s["h_paths"], paths), non_blocking=True)
+            if offsets is not None:
+                s["d_off"].copy_(stage(s["h_off"], offsets), non_blocking=True)
+            if vmax is not None:
+                s["d_vmax"].copy_(stage(s["h_vmax"], vmax), non_blocking=True)
+            s["in_ready"].record(s_in)
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(s["in_ready"])
+            if s["used"]:
+                s_run.wait_event(s["out_done"])
+            self.solver.solve_device(s["d_paths"], s["d_off"] if offsets is not None else None,
+                                     s["d_vmax"] if vmax is not None else None, is_localised, out=s["views"], stream=s_run)
+            s["solved"].record(s_run)
+        tv, _ = sh["bufs"][step % 2]
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(s["solved"])
+            for k in self.fields:
+                tv[k][lo:hi].copy_(s["views"][k], non_blocking=True)
+            # the "delivered" counter travels down the same stream AFTER the data, so it lands after them
+            pp["count"].fill_(step + 1)
+            pp["ctrl_t"][8 * self.rank: 8 * self.rank + 1].copy_(pp["count"], non_blocking=True)
+            s["out_done"].record(s_out)
+        s["used"] = True
+        sh["step"] = step + 1
+        return step
+
+    def wait_host(self, ticket: int):
+        """dst: block until every rank has delivered step `ticket`, return the whole-batch numpy views; others: None."""
+        sh = self._shm
+        if self.rank != self.dst:
+            return None
+        ctrl = sh["ctrl"]
+        for r in range(self.world):
+            while ctrl[8 * r] < ticket + 1:
+                pass
+        return sh["bufs"][ticket % 2][1]

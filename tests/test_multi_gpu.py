@@ -38,13 +38,37 @@ def _worker(rank, world, port_no, transport, B, q):
         sh = ShardedMPC(cfg, fields=FIELDS, device=rank, transport=transport)
         ok, msgs = True, []
         want = BatchedMPC(cfg, device=rank).solve_host(paths, offs, vmax, False, fields=FIELDS) if rank == 0 else None
-        for rep in range(5):
-            out = sh.solve(paths, offs, vmax, False)
+        for rep in range(6):
+            # host delivery alternates between the shared-memory segment (every rank over its own PCIe link) and the
+            # device exchange + one D2H on rank 0
+            out = sh.solve(paths, offs, vmax, False, deliver="shm" if rep & 1 else "exchange")
             if rank == 0:
                 for k in FIELDS:
                     if not np.array_equal(out[k], want[k]):
                         ok = False
                         msgs.append(f"rep {rep} field {k}")
+        lo_, hi_ = sharding.shard_range(B, rank, world)
+        for rep in range(3):                       # shm delivery back to back (both buffers, release counter), local shards
+            out = sh.solve(paths[lo_:hi_], offs[lo_:hi_], vmax[lo_:hi_], False, local=True, B_total=B)
+            if rank == 0 and not all(np.array_equal(out[k], want[k]) for k in FIELDS):
+                ok = False
+                msgs.append(f"shm local rep {rep}")
+        # streams of batches host to host: every rank its own 3-stream pipeline, results through the shared segment
+        prev, n_ok = None, 0
+        for rep in range(6):
+            sc = 1.0 + 0.001 * rep                 # a different batch every step (scaled lateral offsets)
+            tk = sh.submit_host(paths[lo_:hi_], offs[lo_:hi_] * sc, vmax[lo_:hi_], False, B_total=B)
+            if prev is not None:
+                res = sh.wait_host(prev[0])
+                if rank == 0:
+                    ref = BatchedMPC(cfg, device=rank).solve_host(paths, offs * prev[1], vmax, False, fields=["controls", "iters"])
+                    n_ok += int(np.array_equal(res["controls"], ref["controls"]) and np.array_equal(res["iters"], ref["iters"]))
+            prev = (tk, sc)
+        res = sh.wait_host(prev[0])
+        torch.cuda.synchronize()
+        if rank == 0 and n_ok != 5:
+            ok = False
+            msgs.append(f"submit_host / wait_host: {n_ok} of 5 pipelined batches equal the single-GPU solve")
         # device-resident shards, asynchronous, several steps in flight; only the last result is read
         lo, hi = sharding.shard_range(B, rank, world)
         dp = torch.from_numpy(paths[lo:hi]).cuda()
