@@ -574,10 +574,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     if world > 1:
         # Ranks leave an NCCL barrier up to a few hundred microseconds apart, and rank 0's timed region ends only when the
         # LAST rank's results have landed: with 12 ms regions that skew alone is 1-3 % of the figure.  All ranks of one node
-        # share CLOCK_MONOTONIC, so rank 0 publishes a deadline 3 ms ahead and everybody starts on it.
-        go = torch.tensor([time.monotonic_ns() + 3_000_000], dtype=torch.int64, device=dev)
+        # share CLOCK_MONOTONIC, so rank 0 publishes a deadline 20 ms ahead and everybody starts on it.
+        dist.barrier()                      # everybody is HERE before the deadline is drawn (a late rank would start late)
+        go = torch.tensor([time.monotonic_ns() + 20_000_000], dtype=torch.int64, device=dev)
         dist.broadcast(go, src=0)
         go = int(go.item())
+        torch.cuda.synchronize()
         while time.monotonic_ns() < go:
             pass
     sampler.mark()
