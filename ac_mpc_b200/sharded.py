@@ -43,6 +43,10 @@ from .sharding import packed_layout, shard_range
 NBUF = 3
 
 
+class ShmUnavailable(RuntimeError):
+    """The shared host segment of ShardedMPC's host delivery cannot be created (every rank raises it together)."""
+
+
 class _Ticket:
     __slots__ = ("buf", "sizes", "B_total", "step")
 
@@ -89,6 +93,8 @@ class ShardedMPC:
         self._host_out = None
         self._host_sizes = None
         self._shm = None
+        self._shm_failed = False
+        self._want_deliver = "auto"
         self._lv_cache, self._gv_cache, self._size_cache = {}, {}, {}
         self._last_B = 0
 
@@ -292,8 +298,9 @@ class ShardedMPC:
                      over its one PCIe link (79 MB per step at 8 x 4096 instances);
           "auto"     "shm" on CUDA with more than one rank, else "exchange"."""
         torch = self._torch
+        self._want_deliver = deliver
         if deliver == "auto":
-            deliver = "shm" if (self.cuda and self.world > 1) else "exchange"
+            deliver = "shm" if (self.cuda and self.world > 1 and not self._shm_failed) else "exchange"
         paths = np.asarray(paths, dtype=np.float64)
         if local:
             B = paths.shape[0]
@@ -331,8 +338,14 @@ class ShardedMPC:
         if vmax is not None:
             upload(dv, hv, vmax)
         if deliver == "shm":
-            return self._solve_shm(dp, do if offsets is not None else None, dv if vmax is not None else None,
-                                   is_localised, B, B_total, lo, hi)
+            try:
+                return self._solve_shm(dp, do if offsets is not None else None, dv if vmax is not None else None,
+                                       is_localised, B, B_total, lo, hi)
+            except ShmUnavailable as e:          # collective: every rank lands here and takes the exchange path instead
+                if self._want_deliver != "auto":
+                    raise
+                self._shm_failed = True
+                self.transport_note += f" host delivery falls back to the device exchange: {e}"
         t = self.submit_device(dp, do if offsets is not None else None, dv if vmax is not None else None, is_localised,
                                B_total=B_total)
         views = self.wait(t)
@@ -373,8 +386,17 @@ class ShardedMPC:
             offs[k] = (total, nb)
             total = (total + nb + 4095) // 4096 * 4096
         size = 2 * total + 4096
-        name = [uuid.uuid4().hex if self.rank == self.dst else None]
+        name = [None, True]
+        if self.rank == self.dst:
+            name[0] = uuid.uuid4().hex
+            try:      # a container may cap /dev/shm far below what a large batch needs: say so instead of dying on SIGBUS
+                st = os.statvfs("/dev/shm")
+                name[1] = st.f_bavail * st.f_frsize > size + (64 << 20)
+            except OSError:
+                name[1] = False
         dist.broadcast_object_list(name, src=self.dst, group=self.group)
+        if not name[1]:
+            raise ShmUnavailable(f"/dev/shm cannot hold the {size >> 20} MiB result segment")
         path = f"/dev/shm/acmpc_b200_{name[0]}"
         if self.rank == self.dst:
             with open(path, "wb") as f:
