@@ -406,6 +406,18 @@ class ShardedMPC:
         dist.barrier(group=self.group)
         if self.rank == self.dst:
             os.unlink(path)                          # the mappings keep the segment alive
+        # first touch: every rank writes its own slices before anybody pins the segment, so those pages are allocated on
+        # the NUMA node its process runs on (the node its GPU's PCIe link usually hangs off) instead of all on dst's
+        lo_, hi_ = shard_range(B_total, self.rank, self.world)
+        for b in range(2):
+            for k in self.fields:
+                shp, dt = spec[k]
+                o, nb = offs[k]
+                per = nb // max(B_total, 1)
+                mm[b * total + o + lo_ * per: b * total + o + hi_ * per] = 0
+        if self.rank == self.dst:
+            mm[2 * total:] = 0
+        dist.barrier(group=self.group)
         t = torch.from_numpy(mm)
         rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), size, 0)
         if int(rc) != 0:
@@ -524,11 +536,16 @@ class ShardedMPC:
             self.solver.solve_device(s["d_paths"], s["d_off"] if offsets is not None else None,
                                      s["d_vmax"] if vmax is not None else None, is_localised, out=s["views"], stream=s_run)
             s["solved"].record(s_run)
-        tv, _ = sh["bufs"][step % 2]
+        key = ("dst", step % 2, step % pp["depth"])
+        pairs = pp.get(key)
+        if pairs is None:      # (target slice in the segment, device source) per field, built once per buffer pair
+            tv, _ = sh["bufs"][step % 2]
+            pairs = pp[key] = [(tv[k][lo:hi], s["views"][k]) for k in self.fields]
+            pp[("cnt", step % 2)] = pp["ctrl_t"][8 * self.rank: 8 * self.rank + 1]
         with torch.cuda.stream(s_out):
             s_out.wait_event(s["solved"])
-            for k in self.fields:
-                tv[k][lo:hi].copy_(s["views"][k], non_blocking=True)
+            for dst_t, src_t in pairs:
+                dst_t.copy_(src_t, non_blocking=True)
             # the "delivered" counter travels down the same stream AFTER the data, so it lands after them
             pp["count"].fill_(step + 1)
             pp["ctrl_t"][8 * self.rank: 8 * self.rank + 1].copy_(pp["count"], non_blocking=True)
