@@ -233,7 +233,11 @@ class ShardedMPC:
                                           self._credit_table.data_ptr() if self._credit_table is not None else 0,
                                           self.world if self._credit_table is not None else 0, step,
                                           self._credit_local if step >= NBUF else 0, max(step - NBUF + 1, 0))
-            self.solver.solve_device(d_paths, d_offsets, d_vmax, is_localised, out=views, warm=warm, warm_valid=warm_valid)
+            try:
+                self.solver.solve_device(d_paths, d_offsets, d_vmax, is_localised, out=views, warm=warm, warm_valid=warm_valid)
+            except Exception:
+                self.solver.attach_completion()      # nothing was launched: do not leave the one-shot attachment behind
+                raise
             self._step += 1
             self._last_B = B
             return _Ticket(buf, sizes, B_total, step)
