@@ -9,7 +9,10 @@
 //                          its factor in the warp's quarter of the CTA's TENSOR MEMORY allocation (a lane-private
 //                          FP64 scratchpad through tcgen05.ld/st), the cross-lane data in its slice of shared memory
 // The per-instance algorithm is in mpc_warp.cuh; the kernels are instantiated for C = ceil(H/32) = 1..4 horizon
-// stages per lane.
+// stages per lane (C = 3: split layout + CTA-phased rounds, C = 4: one CTA per SM with an L1-friendly carve-out).
+// Host entry points: zero-copy for B <= 64 and for batches in pinned memory (the kernels read / write the host buffers
+// over PCIe), a staged 4-chunk pipeline otherwise.  Multi-GPU: the outputs may be peer-mapped memory of another GPU; the
+// control kernel's last CTA then raises a completion flag there (acmpc_attach_completion).
 //
 // There is NO CPU path in this library: acmpc_create fails with ACMPC_ERR_NO_DEVICE without a GPU.
 #include <vector>

@@ -121,3 +121,23 @@ def test_track_narrower_than_the_car_is_rejected_like_osqp_does():
     b = port.solve_batch(cfg, tight, None, vmax, False, nthreads=2)
     assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iters"], b["iters"])
     assert np.abs(a["controls"] - b["controls"]).max() < 1e-8
+
+
+@pytest.mark.parametrize("H", [33, 64, 65, 80, 96, 97, 128])
+def test_horizon_classes_match_oracle(H):
+    """Every stages-per-lane class and its boundaries: C = 2 (33..64), C = 3 (65..96: the split layout -- cold fields outside
+    shared memory, chunks H2 + NS in shared memory, 32-lane scan matrices), C = 4 (97..128)."""
+    import _golden
+    from ac_mpc_b200 import tracks
+
+    kw = _golden.racing_kwargs("spa", H)
+    paths, vmax = tracks.perturbed_batch("spa", 6, horizon=H, seed=H)
+    cfg = port.default_config(**kw)
+    a = _emul.solve_batch(cfg, paths, None, vmax, False)
+    b = port.solve_batch(cfg, paths, None, vmax, False, nthreads=4)
+    for k in ("status", "status_speed", "iters", "rho_updates"):
+        assert np.array_equal(a[k], b[k]), k
+    ok = b["status"] == 1
+    for k in ("controls", "states", "v_ref", "prediction", "derived"):
+        np.testing.assert_allclose(a[k][ok], b[k][ok], rtol=0, atol=1e-8, err_msg=k)
+    np.testing.assert_allclose(a["cost"], b["cost"], rtol=1e-7, atol=1e-7)
