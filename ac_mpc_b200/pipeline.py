@@ -52,12 +52,15 @@ class HostPipeline:
             self.slots.append(slot)
         self._n = 0
 
-    def _stage(self, stage, arr):
-        """A host tensor the copy engine can read asynchronously: the caller's array if it is pinned, else a staged copy."""
+    def _stage(self, slot, stage, arr):
+        """A host tensor the copy engine can read asynchronously: the caller's array if it is pinned, else a staged copy
+        (made only once the previous upload FROM this slot's staging buffer has left it)."""
         torch = self._torch
         src = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
         if src.is_pinned():
             return src
+        if slot["used"]:
+            slot["in_ready"].synchronize()
         stage[: src.shape[0]].copy_(src)
         return stage[: src.shape[0]]
 
@@ -70,11 +73,11 @@ class HostPipeline:
         with torch.cuda.stream(self.s_in):
             if s["used"]:
                 self.s_in.wait_event(s["solved"])       # the kernels that read this slot's inputs are done
-            s["d_paths"].copy_(self._stage(s["h_paths"], paths), non_blocking=True)
+            s["d_paths"].copy_(self._stage(s, s["h_paths"], paths), non_blocking=True)
             if offsets is not None:
-                s["d_off"].copy_(self._stage(s["h_off"], offsets), non_blocking=True)
+                s["d_off"].copy_(self._stage(s, s["h_off"], offsets), non_blocking=True)
             if vmax is not None:
-                s["d_vmax"].copy_(self._stage(s["h_vmax"], vmax), non_blocking=True)
+                s["d_vmax"].copy_(self._stage(s, s["h_vmax"], vmax), non_blocking=True)
             s["in_ready"].record(self.s_in)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(s["in_ready"])

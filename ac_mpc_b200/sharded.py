@@ -521,6 +521,8 @@ class ShardedMPC:
             src = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
             if src.is_pinned():
                 return src
+            if s["used"]:
+                s["in_ready"].synchronize()     # the previous upload from this staging buffer has left it
             buf.copy_(src)
             return buf
 
